@@ -1,0 +1,289 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Thin C-ABI driver around the UNMODIFIED reference library (DCM-UPB/MCIntegratorPlusPlus). It is compiled
+// by oracle/Makefile together with the reference's own sources *where they lie* under /root/reference
+// (nothing is copied into this repo) into oracle/_ref/libmci_ref.so. It exists to
+//   (1) pin the plain-C restatement (oracle/mci_oracle.c) against the real implementation, bit for bit, and
+//   (2) generate the golden vectors committed under tests/golden/ (tools: oracle/gen_golden.py).
+// The product library never links, loads or calls this file.
+//
+// All std headers are included BEFORE the `private -> public` switch, which is applied only to the
+// reference's own headers so that the harness can read MCI's walker state / RNG inside the step callback
+// (access specifiers do not change class layout, the library itself is compiled untouched).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <array>
+
+#define private public
+#define protected public
+#include "mci/MCIntegrator.hpp"
+#include "mci/Estimators.hpp"
+#include "mci/MJBlocker.hpp"
+#include "mci/OrthoPeriodicDomain.hpp"
+#include "mci/UnboundDomain.hpp"
+#include "TestMCIFunctions.hpp"   // /root/reference/test/common
+#include "ExampleFunctions.hpp"   // /root/reference/examples/common
+#undef private
+#undef protected
+
+#include "oracle_config.h"
+
+using namespace mci;
+
+static thread_local std::string g_err;
+
+static std::unique_ptr<SamplingFunctionInterface> make_pdf(int id, int ndim)
+{
+    switch (id) {
+    case ORC_PDF_GAUSS3D: return std::make_unique<ThreeDimGaussianPDF>();
+    case ORC_PDF_GAUSS: return std::make_unique<Gauss>(ndim);
+    case ORC_PDF_EXP1D: return std::make_unique<Exp1DPDF>();
+    case ORC_PDF_EXPND: return std::make_unique<ExpNDPDF>(ndim);
+    case ORC_PDF_NORMLINE: return std::make_unique<NormalizedLine>();
+    default: throw std::invalid_argument("ref_harness: unknown pdf id");
+    }
+}
+
+static std::unique_ptr<ObservableFunctionInterface> make_obs(int id, int ndim)
+{
+    switch (id) {
+    case ORC_OBS_XSQUARED: return std::make_unique<XSquared>();
+    case ORC_OBS_GAUSSXSQUARED: return std::make_unique<GaussXSquared>();
+    case ORC_OBS_XYZSQUARED: return std::make_unique<XYZSquared>();
+    case ORC_OBS_X1D: return std::make_unique<X1D>();
+    case ORC_OBS_XND: return std::make_unique<XND>(ndim);
+    case ORC_OBS_UPDXND: return std::make_unique<UpdateableXND>(ndim);
+    case ORC_OBS_CONSTVAL: return std::make_unique<Constval>(ndim);
+    case ORC_OBS_POLYNOM: return std::make_unique<Polynom>(ndim);
+    case ORC_OBS_X2SUM: return std::make_unique<X2Sum>(ndim);
+    case ORC_OBS_X2: return std::make_unique<X2>(ndim);
+    case ORC_OBS_PARABOLA: return std::make_unique<Parabola>();
+    case ORC_OBS_NORMPARABOLA: return std::make_unique<NormalizedParabola>();
+    default: throw std::invalid_argument("ref_harness: unknown obs id");
+    }
+}
+
+static EstimatorType to_estim(int t)
+{
+    switch (t) {
+    case ORC_EST_NOOP: return EstimatorType::Noop;
+    case ORC_EST_UNCORRELATED: return EstimatorType::Uncorrelated;
+    case ORC_EST_CORRELATED: return EstimatorType::Correlated;
+    case ORC_EST_FCBLOCKER: return EstimatorType::FCBlocker;
+    case ORC_EST_MJBLOCKER: return EstimatorType::MJBlocker;
+    default: throw std::invalid_argument("ref_harness: unknown estimator type");
+    }
+}
+
+static void configure(MCI &mci, const orc_config_t &c)
+{
+    mci.setSeed(c.seed);
+    if (c.domain == ORC_DOMAIN_ORTHO) { mci.setIRange(c.lb, c.ub); }
+    // move
+    const int ntypes = std::max(1, c.ntypes);
+    std::vector<int> tends(c.type_ends, c.type_ends + ORC_MAXTYPES);
+    if (c.srrd != ORC_SRRD_UNIFORM && c.srrd != ORC_SRRD_GAUSSIAN) { throw std::invalid_argument("ref_harness: unsupported srrd"); }
+    const SRRDType srrd = (c.srrd == ORC_SRRD_GAUSSIAN) ? SRRDType::Gaussian : SRRDType::Uniform;
+    if (c.move_type == ORC_MOVE_ALL) {
+        mci.setTrialMove(srrd, 0, ntypes, ntypes > 1 ? tends.data() : nullptr);
+    }
+    else if (c.move_type == ORC_MOVE_VEC) {
+        mci.setTrialMove(srrd, std::max(1, c.veclen), ntypes, ntypes > 1 ? tends.data() : nullptr);
+    }
+    else if (c.move_type == ORC_MOVE_MULTISTEP) {
+        // MultiStepMove with a uniform single-vector sub-move (its default kind, MultiStepMove.hpp:46-52)
+        MultiStepMove msm(c.ndim, c.ms_nsteps > 0 ? c.ms_nsteps : c.ndim);
+        const int veclen = std::max(1, c.veclen);
+        if (ntypes > 1) {
+            UniformVecMove sub(c.ndim/veclen, veclen, ntypes, tends.data(), DEFAULT_MRT2STEP);
+            msm.setTrialMove(sub);
+        }
+        else {
+            UniformVecMove sub(c.ndim/veclen, veclen, DEFAULT_MRT2STEP);
+            msm.setTrialMove(sub);
+        }
+        if (c.ms_sub_pdf_id != ORC_PDF_NONE) { msm.addSamplingFunction(*make_pdf(c.ms_sub_pdf_id, c.ndim)); }
+        mci.setTrialMove(msm);
+    }
+    else { throw std::invalid_argument("ref_harness: unknown move type"); }
+    for (int i = 0; i < ntypes; ++i) { mci.setMRT2Step(i, c.steps[i]); }
+
+    mci.setX(c.x0);
+    if (c.pdf_id != ORC_PDF_NONE) { mci.addSamplingFunction(make_pdf(c.pdf_id, c.ndim)); }
+    for (int i = 0; i < c.nobs; ++i) {
+        mci.addObservable(make_obs(c.obs[i].obs_id, c.ndim), c.obs[i].blocksize, c.obs[i].nskip,
+                          c.obs[i].flag_equil != 0, to_estim(c.obs[i].estim_type));
+    }
+    mci.setTargetAcceptanceRate(c.target_acc);
+    mci.setNfindMRT2Iterations(c.nfind);
+    mci.setNdecorrelationSteps(c.ndecorr);
+}
+
+// Replays the libstdc++ distribution OUTPUTS the main run is going to consume, from a copy of
+// MCI's generator taken right before the main run. The reference's own results prove the contract: the C oracle
+// consumes exactly this stream and must reproduce avg/acc/x bit for bit.
+static int64_t export_draws(const orc_config_t &c, std::mt19937_64 g /*copy*/, double * out, int64_t cap)
+{
+    std::uniform_real_distribution<double> rsym(-1., 1.), r01(0., 1.);
+    const int veclen = std::max(1, c.veclen);
+    std::uniform_int_distribution<int> ridx(0, c.ndim/veclen - 1);
+    int64_t n = 0;
+    auto put = [&](double v) { if (n < cap) { out[n] = v; } ++n; };
+    if (c.srrd != ORC_SRRD_UNIFORM) { return -1; } // gaussian draws are stateful in libstdc++ (cached second value): not exported
+    for (int64_t s = 0; s < c.nmc; ++s) {
+        if (c.pdf_id == ORC_PDF_NONE) { // doStepRandom: ndim x U(0,1)   src/MCIntegrator.cpp:365
+            for (int i = 0; i < c.ndim; ++i) { put(r01(g)); }
+            continue;
+        }
+        if (c.move_type == ORC_MOVE_ALL) {
+            for (int i = 0; i < c.ndim; ++i) { put(rsym(g)); }
+        }
+        else if (c.move_type == ORC_MOVE_VEC) {
+            put(static_cast<double>(ridx(g)));
+            for (int i = 0; i < veclen; ++i) { put(rsym(g)); }
+        }
+        else {
+            const int nsub = c.ms_nsteps > 0 ? c.ms_nsteps : c.ndim;
+            for (int k = 0; k < nsub; ++k) {
+                put(static_cast<double>(ridx(g)));
+                for (int i = 0; i < veclen; ++i) { put(rsym(g)); }
+                put(r01(g));
+            }
+        }
+        put(r01(g)); // accept draw, always consumed   src/MCIntegrator.cpp:343
+    }
+    return n;
+}
+
+extern "C" {
+
+const char * mciref_last_error() { return g_err.c_str(); }
+
+// Runs integrate() exactly as a user of the reference would; returns 0 on success.
+int mciref_run(const orc_config_t * cfg, orc_result_t * res, orc_trace_t * trace)
+{
+    try {
+        const orc_config_t &c = *cfg;
+        MCI mci(c.ndim);
+        configure(mci, c);
+        const int nobsdim = mci.getNObsDim();
+        if (nobsdim > ORC_MAXOBSDIM) { throw std::invalid_argument("ref_harness: nobsdim too large"); }
+        std::vector<double> avg(std::max(1, nobsdim), 0.), err(std::max(1, nobsdim), 0.);
+
+        if (trace != nullptr) {
+            // split integrate() into its two halves (calibration/decorrelation, then main run): same call sequence
+            // as one integrate(nmc, ..., do_find, do_decorr)   src/MCIntegrator.cpp:49-63
+            mci.integrate(0, avg.data(), err.data(), c.do_find != 0, c.do_decorr != 0);
+            trace->n_draws = export_draws(c, mci._rgen, trace->draws, trace->cap_draws);
+            int64_t istep = -1; // first callback comes from initializeSampling()   src/MCIntegrator.cpp:267
+            mci.setCallback([&](const MCI &m) {
+                if (istep >= 0 && istep < trace->cap_steps) { trace->accepted[istep] = m._wlkstate.accepted ? 1 : 0; }
+                ++istep;
+            });
+            mci.integrate(c.nmc, avg.data(), err.data(), false, false);
+            mci.clearCallback();
+            trace->n_steps = istep;
+        }
+        else {
+            mci.integrate(c.nmc, avg.data(), err.data(), c.do_find != 0, c.do_decorr != 0);
+        }
+
+        std::memset(res, 0, sizeof(*res));
+        res->nobsdim = nobsdim;
+        std::copy(avg.begin(), avg.begin() + nobsdim, res->avg);
+        std::copy(err.begin(), err.begin() + nobsdim, res->err);
+        res->acc_rate = mci.getAcceptanceRate();
+        for (int i = 0; i < c.ndim; ++i) { res->x_final[i] = mci.getX(i); }
+        for (int i = 0; i < std::max(1, c.ntypes); ++i) { res->steps_final[i] = mci.getMRT2Step(i); }
+        res->n_acc = mci._acc;
+        res->n_rej = mci._rej;
+        return 0;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Direct access to the reference estimators (include/mci/Estimators.hpp:9-45). nblocks is only used by BLOCK (=100).
+int mciref_estimate(int estim_type, int64_t n, int ndim, const double * x, int64_t nblocks, double * avg, double * err)
+{
+    try {
+        switch (estim_type) {
+        case ORC_EST_NOOP: NoopEstimator(n, ndim, x, avg, err); break;
+        case ORC_EST_UNCORRELATED: UncorrelatedEstimator(n, ndim, x, avg, err); break;
+        case ORC_EST_CORRELATED: CorrelatedEstimator(n, ndim, x, avg, err); break;
+        case ORC_EST_FCBLOCKER: FCBlockerEstimator(n, ndim, x, avg, err); break;
+        case ORC_EST_MJBLOCKER: MJBlockerEstimator(n, ndim, x, avg, err); break;
+        case 100:
+            if (ndim > 1) { MultiDimBlockEstimator(n, ndim, x, nblocks, avg, err); }
+            else { OneDimBlockEstimator(n, x, nblocks, avg[0], err[0]); }
+            break;
+        default: throw std::invalid_argument("ref_harness: unknown estimator");
+        }
+        return 0;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// TestWalk fixture (test/common/TestMCIFunctions.hpp:14-118): rand()-driven walk used by ut1 and bench_estimators.
+// pdf: 0 = SLATER, 1 = GAUSS. Calls srand(seed) first. Returns the acceptance rate.
+double mciref_testwalk(int pdf, int nmc, int ndim, double step, double change_prob, unsigned seed, double * datax,
+                       uint8_t * datacc, int * nchanged, int * changed_idx)
+{
+    srand(seed);
+    static_assert(sizeof(bool) == 1, "bool size");
+    if (pdf == 0) {
+        TestWalk<WalkPDF::SLATER> tw(nmc, ndim, step, change_prob);
+        tw.generateWalk(datax, reinterpret_cast<bool *>(datacc), nchanged, changed_idx);
+        return tw.getAcceptanceRate();
+    }
+    TestWalk<WalkPDF::GAUSS> tw(nmc, ndim, step, change_prob);
+    tw.generateWalk(datax, reinterpret_cast<bool *>(datacc), nchanged, changed_idx);
+    return tw.getAcceptanceRate();
+}
+
+// Drives one reference accumulator by hand through a recorded walk, the way test/ut1/main.cpp:116-139 does.
+// Returns nstore; data_out must hold nstore*nobs doubles (query with data_out == nullptr first).
+int64_t mciref_accumulate(int obs_id, int ndim, int blocksize, int nskip, int64_t nmc, const double * datax,
+                          const uint8_t * datacc, const int * nchanged, const int * changed_idx, double * data_out)
+{
+    try {
+        auto obs = make_obs(obs_id, ndim);
+        auto accu = createAccumulator(*obs, blocksize, nskip);
+        accu->allocate(nmc);
+        WalkerState wlk(ndim, true);
+        for (int64_t i = 0; i < nmc; ++i) {
+            std::copy(datax + i*ndim, datax + (i + 1)*ndim, wlk.xnew);
+            wlk.accepted = datacc[i] != 0;
+            wlk.nchanged = nchanged[i];
+            std::copy(changed_idx + i*ndim, changed_idx + i*ndim + wlk.nchanged, wlk.changedIdx);
+            accu->accumulate(wlk);
+        }
+        accu->finalize();
+        const int64_t nstore = accu->getNStore();
+        if (data_out != nullptr) { std::copy(accu->getData(), accu->getData() + nstore*accu->getNObs(), data_out); }
+        return nstore;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+} // extern "C"
