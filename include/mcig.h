@@ -1,0 +1,156 @@
+/* mcig.h — C-ABI of the B200-native Monte Carlo integration engine (libmcig.so).
+ *
+ * This is the drop-in boundary for the sampling path of DCM-UPB/MCIntegratorPlusPlus. Every entry point names the
+ * reference interface it replaces (paths relative to the reference repository). The C++ facade in include/mci/ is
+ * implemented on top of these calls, so reference-style programs recompile against it unchanged.
+ *
+ * Conventions: plain pointers and sizes only; all pointers are caller-owned; a context owns its device memory; calls
+ * are blocking; a context is single-threaded like the reference's MCI object. Functions returning int yield 0 on
+ * success or an MCIG_ERR_* code, with the message available from mcig_last_error(); the codes map one-to-one onto
+ * the std exceptions the reference throws (SURVEY.md §8b "Error conventions").
+ *
+ * There is NO CPU fallback: every call that samples or estimates fails with MCIG_ERR_CUDA if no sm_100 device or no
+ * CUDA driver is available.
+ */
+#ifndef MCIG_H
+#define MCIG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcig_ctx mcig_ctx;
+
+enum {
+    MCIG_OK = 0,
+    MCIG_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument */
+    MCIG_ERR_DOMAIN = 2,           /* std::domain_error */
+    MCIG_ERR_RUNTIME = 3,          /* std::runtime_error */
+    MCIG_ERR_CUDA = 4              /* CUDA / NVRTC failure (no reference analogue) */
+};
+
+/* include/mci/Factories.hpp:108-145 */
+enum { MCIG_MOVE_ALL = 0, MCIG_MOVE_VEC = 1, MCIG_MOVE_MULTISTEP = 2 };
+enum { MCIG_SRRD_UNIFORM = 0 };
+/* include/mci/Factories.hpp:52-59 */
+enum { MCIG_EST_NOOP = 0, MCIG_EST_UNCORRELATED = 1, MCIG_EST_CORRELATED = 2, MCIG_EST_FCBLOCKER = 3, MCIG_EST_MJBLOCKER = 4 };
+/* random number source of the walk kernel */
+enum {
+    MCIG_RNG_PHILOX32 = 0, /* Philox4x32-10, one 32-bit word per uniform (production default) */
+    MCIG_RNG_PHILOX53 = 1, /* Philox4x32-10, 52-bit uniforms */
+    MCIG_RNG_REPLAY = 2    /* per-walker std::mt19937_64 + libstdc++ distributions generated on the host and consumed by
+                              the kernel in the reference's order: bit-exact reference trajectories (parity mode) */
+};
+enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1 };
+
+const char * mcig_last_error(void);
+int mcig_version(void);
+/* number of usable CUDA devices (0 when there is no driver / GPU) */
+int mcig_device_count(void);
+
+/* ---- plugin registry: ProtoFunctionInterface / SamplingFunctionInterface / ObservableFunctionInterface subclasses
+ *      (include/mci/SamplingFunctionInterface.hpp:36-105, ObservableFunctionInterface.hpp:30-63) re-expressed as
+ *      __device__ functors. `source` is CUDA C++ pasted into the JIT translation unit (may be NULL for built-ins),
+ *      `type_expr` the functor type with "{ndim}" substituted (e.g. "mcig_builtin::Gauss<{ndim}>").
+ *      ndim == 0: any dimension; nvalues == 0: nproto / nobs equals ndim. Returns the plugin id (>= 0) or -1. */
+int mcig_register_plugin(int kind, const char * name, const char * type_expr, const char * source, int ndim, int nvalues,
+                         int npar, int has_update, int elementwise);
+/* id of a registered plugin (the reference's fixtures are pre-registered under their class names), or -1 */
+int mcig_lookup_plugin(int kind, const char * name);
+
+/* ---- construction: MCI::MCI(int ndim)  src/MCIntegrator.cpp:624-649 (same defaults) */
+mcig_ctx * mcig_create(int ndim);
+void mcig_destroy(mcig_ctx * ctx);
+int mcig_set_device(mcig_ctx * ctx, int device);
+
+/* ---- MCI::setSeed  src/MCIntegrator.cpp:547-550. Philox modes: the key. Replay mode: walker w is seeded with seed
+ *      unless per-walker seeds are given (MPIMCI::setSeed, src/MPIMCI.cpp:38-65: rank r <- seed file entry offset+r). */
+int mcig_set_seed(mcig_ctx * ctx, uint64_t seed);
+int mcig_set_walker_seeds(mcig_ctx * ctx, const uint64_t * seeds, int64_t n);
+int mcig_set_rng_mode(mcig_ctx * ctx, int mode);
+
+/* ---- walkers: one reference MCI = one chain; many chains exist there only as MPI ranks (src/MPIMCI.cpp:83).
+ *      Here one context runs W chains ("virtual ranks"). global_offset / total describe the shard of a multi-GPU job. */
+int mcig_set_walkers(mcig_ctx * ctx, int64_t nwalkers, int64_t global_offset, int64_t total_walkers);
+int64_t mcig_get_walkers(mcig_ctx * ctx);
+
+/* ---- positions: MCI::setX / getX / centerX / newRandomX / moveX  src/MCIntegrator.cpp:594-619 */
+int mcig_set_x(mcig_ctx * ctx, const double * x /*[ndim], broadcast to all walkers*/);
+int mcig_set_x_walkers(mcig_ctx * ctx, const double * x /*[nwalkers][ndim]*/);
+int mcig_get_x(mcig_ctx * ctx, int64_t walker, double * x /*[ndim]*/);
+
+/* ---- domain: MCI::resetDomain / setIRange  src/MCIntegrator.cpp:390-408 */
+int mcig_set_domain_unbound(mcig_ctx * ctx);
+int mcig_set_domain_ortho(mcig_ctx * ctx, const double * lbounds, const double * ubounds);
+
+/* ---- trial move: MCI::setTrialMove(MoveType) / (SRRDType, veclen, ntypes, typeEnds)  src/MCIntegrator.cpp:423-446.
+ *      Step sizes are reset to DEFAULT_MRT2STEP = 0.05 (Factories.hpp:145). MultiStep: sub-move = uniform single-vector
+ *      move of length veclen, nsteps <= 0 means ndim (MultiStepMove.hpp:46-52); its own sampling functions are added
+ *      with mcig_multistep_add_pdf (MultiStepMove::addSamplingFunction). */
+int mcig_set_move(mcig_ctx * ctx, int move_type, int srrd, int veclen, int ntypes, const int * type_ends);
+int mcig_multistep_config(mcig_ctx * ctx, int nsteps);
+int mcig_multistep_add_pdf(mcig_ctx * ctx, int plugin_id, const double * par, int npar);
+/* MCI::setMRT2Step / getMRT2Step  src/MCIntegrator.cpp:557-585 */
+int mcig_get_nsteps_sizes(mcig_ctx * ctx);
+int mcig_set_step(mcig_ctx * ctx, int i, double step);
+double mcig_get_step(mcig_ctx * ctx, int i);
+
+/* ---- sampling functions / observables: MCI::addSamplingFunction, addObservable(obs, blocksize, nskip, flag_equil,
+ *      EstimatorType), pop*, clear*  src/MCIntegrator.cpp:451-490 */
+int mcig_add_pdf(mcig_ctx * ctx, int plugin_id, const double * par, int npar);
+int mcig_pop_pdf(mcig_ctx * ctx);
+int mcig_clear_pdfs(mcig_ctx * ctx);
+int mcig_add_obs(mcig_ctx * ctx, int plugin_id, const double * par, int npar, int blocksize, int nskip, int flag_equil, int estim_type);
+int mcig_pop_obs(mcig_ctx * ctx);
+int mcig_clear_obs(mcig_ctx * ctx);
+int mcig_get_nobsdim(mcig_ctx * ctx);
+
+/* ---- automatic routines: setTargetAcceptanceRate / setNfindMRT2Iterations / setNdecorrelationSteps
+ *      include/mci/MCIntegrator.hpp:113-123 (N<0 auto with max |N|, 0 off, N>0 fixed) */
+int mcig_set_autotune(mcig_ctx * ctx, int nfind_iterations, int64_t ndecorrelation_steps, double target_acceptance);
+
+/* ---- optional cross-process sum (the MPI_Allreduce(SUM) of src/MCIntegrator.cpp:21-34, :135 and src/MPIMCI.cpp:85-87).
+ *      When set, the engine calls it for the acceptance rate during calibration, for the estimates during automatic
+ *      decorrelation and for the final [sum avg | sum err^2] so that a job sharded over several processes/GPUs behaves
+ *      like one MPI job. buf is a host array of n doubles, summed in place over all processes. */
+typedef void (*mcig_allreduce_fn)(double * buf, int n, void * user);
+int mcig_set_allreduce(mcig_ctx * ctx, mcig_allreduce_fn fn, void * user);
+
+/* ---- MCI::integrate(Nmc, average, error, doFindMRT2step, doDecorrelation)  src/MCIntegrator.cpp:43-82, combined over
+ *      walkers as MPIMCI::integrate does over ranks (src/MPIMCI.cpp:85-92): avg = sum_w avg_w / W, err = sqrt(sum_w err_w^2) / W */
+int mcig_integrate(mcig_ctx * ctx, int64_t nmc, double * average, double * error, int do_find_mrt2_step, int do_decorrelation);
+/* MCI::getAcceptanceRate  src/MCIntegrator.cpp:587-592 (of the last sampling run, over all walkers) */
+double mcig_get_acceptance_rate(mcig_ctx * ctx);
+
+/* ---- results of the last integrate beyond the reference's API */
+int mcig_get_walker_results(mcig_ctx * ctx, double * avg /*[nobsdim][nwalkers]*/, double * err /*same*/);
+/* local sums [sum_w avg_w | sum_w err_w^2 | sum_w avg_w^2], 3*nobsdim doubles: the all-reduce payload of a sharded job */
+int mcig_get_sums(mcig_ctx * ctx, double * sums);
+/* standard error of the mean over walkers, sqrt((<a^2>-<a>^2)/(W-1)) (local walkers) */
+int mcig_get_cross_walker_error(mcig_ctx * ctx, double * err);
+/* stored samples of observable iobs of the last integrate (Block/Full accumulators), host order [nstore][nobs] of one walker */
+int64_t mcig_get_nstore(mcig_ctx * ctx, int iobs);
+int mcig_get_obs_data(mcig_ctx * ctx, int iobs, int64_t walker, double * data);
+/* device times of the last integrate in ms (CUDA events on the engine's stream): the walk kernel of the main sampling run,
+ * the estimation stage, the whole call (calibration + decorrelation + sampling + estimation); and the kernels it launched */
+int mcig_get_timings(mcig_ctx * ctx, double * walk_ms, double * estim_ms, double * total_ms, int64_t * kernel_launches);
+
+/* ---- estimators on host data (include/mci/Estimators.hpp:9-45): data x[n][ndim], run on the device */
+int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double * average, double * error);
+
+/* ---- engine knobs without reference analogue */
+int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
+int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory */
+/* compile (JIT) the kernels the current configuration needs without running them; works without a GPU */
+int mcig_prebuild(mcig_ctx * ctx);
+/* generated CUDA source of the main walk kernel (for inspection); returns bytes needed */
+int64_t mcig_get_kernel_source(mcig_ctx * ctx, char * buf, int64_t cap);
+/* issue-rate microbenchmarks (roofline denominators): DFMA/s and IMAD/s of the current device */
+int mcig_measure_peaks(int device, double * dfma_per_s, double * imad_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,287 @@
+// mcig_functors.cuh — built-in sampling-function / observable functors: the reference's own fixtures re-expressed as
+// __device__ functors (test/common/TestMCIFunctions.hpp:123-473, examples/common/ExampleFunctions.hpp:11-82).
+//
+// Plugin contract (what a user-supplied functor source must look like; it is pasted into the JIT translation unit):
+//
+//   struct MyPDF {                                  // mirrors mci::SamplingFunctionInterface
+//       static constexpr int NPAR = 0;              // doubles of run-time parameters (passed as `par`)
+//       static constexpr bool HAS_UPDATE = false;   // overrides updatedAcceptance? (else full recompute is used)
+//       static constexpr bool ELEMENTWISE = false;  // proto value k depends on x[k] only and updatedAcceptance touches
+//                                                   // protonew[changedIdx] only (lets the smem path commit O(nchanged))
+//       const double * par;
+//       template <class X, class P> __device__ void protoFunction(const X & in, P & pv) const;
+//       template <class P> __device__ double samplingFunction(const P & pv) const;
+//       template <class PO, class PN> __device__ double acceptanceFunction(const PO & po, const PN & pn) const;
+//       template <class W, class PO, class PN> __device__ double updatedAcceptance(const W & wlk, const PO & po, PN & pn) const;
+//   };
+//   struct MyObs {                                  // mirrors mci::ObservableFunctionInterface
+//       static constexpr int NPAR = 0;
+//       const double * par;
+//       template <class X, class O> __device__ void observableFunction(const X & in, O & out) const;
+//   };
+//
+// X / P / O are array-like (double* or a strided shared-memory view): index them with [], nothing else.
+// ndim / nproto / nobs are declared to the host through the C-ABI registration (include/mcig.h).
+//
+// Arithmetic note: expressions keep the reference's operation order so that the replay mode (compiled with
+// --fmad=false) reproduces the CPU bits; XSquared multiplies by the reciprocal instead of dividing by 3 (an FP64
+// division costs ~20 issue slots on the device): <= 1 ulp per sample, inside the 1e-12 sum tolerance.
+#pragma once
+#include "mcig_device.cuh"
+
+namespace mcig_builtin {
+
+using mcig::exp;
+
+// ---------------------------------------------------------------- sampling functions
+struct ThreeDimGaussianPDF { // TestMCIFunctions.hpp:123-148 (ndim 3, nproto 1)
+    static constexpr int NPAR = 0;
+    static constexpr bool HAS_UPDATE = false;
+    static constexpr bool ELEMENTWISE = false;
+    const double * par;
+    template <class X, class P>
+    MCIG_DEV void protoFunction(const X & in, P & pv) const { pv[0] = in[0]*in[0] + in[1]*in[1] + in[2]*in[2]; }
+    template <class P>
+    MCIG_DEV double samplingFunction(const P & pv) const { return exp(-pv[0]); }
+    template <class PO, class PN>
+    MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const { return exp(-pn[0] + po[0]); }
+};
+
+template <int NDIM>
+struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
+    static constexpr int NPAR = 0;
+    static constexpr bool HAS_UPDATE = true;
+    static constexpr bool ELEMENTWISE = true;
+    const double * par;
+    template <class X, class P>
+    MCIG_DEV void protoFunction(const X & in, P & pv) const
+    {
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { pv[i] = in[i]*in[i]; }
+    }
+    template <class P>
+    MCIG_DEV double samplingFunction(const P & pv) const
+    {
+        double s = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { s += pv[i]; }
+        return exp(-s);
+    }
+    template <class PO, class PN>
+    MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
+    {
+        double a = 0., b = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { a += po[i]; }
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
+        return exp(a - b);
+    }
+    template <class W, class PO, class PN>
+    MCIG_DEV double updatedAcceptance(const W & wlk, const PO & po, PN & pn) const
+    {
+        double expf = 0.;
+        for (int i = 0; i < wlk.nchanged; ++i) {
+            const int k = wlk.changedIdx[i];
+            const double xk = wlk.xnew[k];
+            const double v = xk*xk;
+            pn[k] = v;
+            expf += v - po[k];
+        }
+        return exp(-expf);
+    }
+};
+
+struct Exp1DPDF { // TestMCIFunctions.hpp:189-215
+    static constexpr int NPAR = 0;
+    static constexpr bool HAS_UPDATE = false;
+    static constexpr bool ELEMENTWISE = false;
+    const double * par;
+    template <class X, class P>
+    MCIG_DEV void protoFunction(const X & in, P & pv) const { pv[0] = fabs(in[0]); }
+    template <class P>
+    MCIG_DEV double samplingFunction(const P & pv) const { return exp(-pv[0]); }
+    template <class PO, class PN>
+    MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const { return exp(-pn[0] + po[0]); }
+};
+
+template <int NDIM>
+struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
+    static constexpr int NPAR = 0;
+    static constexpr bool HAS_UPDATE = true;
+    static constexpr bool ELEMENTWISE = true;
+    const double * par;
+    template <class X, class P>
+    MCIG_DEV void protoFunction(const X & in, P & pv) const
+    {
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { pv[i] = fabs(in[i]); }
+    }
+    template <class P>
+    MCIG_DEV double samplingFunction(const P & pv) const
+    {
+        double s = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { s += pv[i]; }
+        return exp(-s);
+    }
+    template <class PO, class PN>
+    MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
+    {
+        double a = 0., b = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { a += po[i]; }
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
+        return exp(a - b);
+    }
+    template <class W, class PO, class PN>
+    MCIG_DEV double updatedAcceptance(const W & wlk, const PO & po, PN & pn) const
+    {
+        double expf = 0.;
+        for (int i = 0; i < wlk.nchanged; ++i) {
+            const int k = wlk.changedIdx[i];
+            const double v = fabs(wlk.xnew[k]);
+            pn[k] = v;
+            expf += v - po[k];
+        }
+        return exp(-expf);
+    }
+};
+
+struct NormalizedLine { // ExampleFunctions.hpp:54-82 (not an exponential family: acceptance is a plain ratio)
+    static constexpr int NPAR = 0;
+    static constexpr bool HAS_UPDATE = false;
+    static constexpr bool ELEMENTWISE = false;
+    const double * par;
+    template <class X, class P>
+    MCIG_DEV void protoFunction(const X & in, P & pv) const { pv[0] = 0.2*fabs(in[0]); }
+    template <class P>
+    MCIG_DEV double samplingFunction(const P & pv) const { return pv[0]; }
+    template <class PO, class PN>
+    MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
+    {
+        if (po[0] == 0.) { return (pn[0] != 0.) ? 1. : 0.; }
+        return pn[0]/po[0];
+    }
+};
+
+// ---------------------------------------------------------------- observables
+struct XSquared { // TestMCIFunctions.hpp:260-275
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const { out[0] = (in[0]*in[0] + in[1]*in[1] + in[2]*in[2])*(1./3.); }
+};
+
+struct GaussXSquared { // TestMCIFunctions.hpp:278-296
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+        const double normf = 0.059862374041722184; // 1./sqrt(M_PI*M_PI*M_PI)/3.
+        const double x2 = in[0]*in[0] + in[1]*in[1] + in[2]*in[2];
+        out[0] = exp(-x2)*x2*normf;
+    }
+};
+
+struct XYZSquared { // TestMCIFunctions.hpp:299-317
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+        out[0] = in[0]*in[0];
+        out[1] = in[1]*in[1];
+        out[2] = in[2]*in[2];
+    }
+};
+
+struct X1D { // TestMCIFunctions.hpp:320-336
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const { out[0] = in[0]; }
+};
+
+template <int NDIM>
+struct XND { // TestMCIFunctions.hpp:339-379 (XND and UpdateableXND compute the same values)
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { out[i] = in[i]; }
+    }
+};
+
+struct Constval { // TestMCIFunctions.hpp:382-398
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X &, O & out) const { out[0] = 1.3; }
+};
+
+template <int NDIM>
+struct Polynom { // TestMCIFunctions.hpp:401-420
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+        double s = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { s += in[i]; }
+        out[0] = s;
+    }
+};
+
+template <int NDIM>
+struct X2Sum { // TestMCIFunctions.hpp:423-442
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+        double s = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { s += in[i]*in[i]; }
+        out[0] = s;
+    }
+};
+
+template <int NDIM>
+struct X2 { // TestMCIFunctions.hpp:445-473
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { out[i] = in[i]*in[i]; }
+    }
+};
+
+struct Parabola { // ExampleFunctions.hpp:11-29
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const { out[0] = 4.*in[0] - in[0]*in[0]; }
+};
+
+struct NormalizedParabola { // ExampleFunctions.hpp:32-50
+    static constexpr int NPAR = 0;
+    const double * par;
+    template <class X, class O>
+    MCIG_DEV void observableFunction(const X & in, O & out) const
+    {
+        const double x = in[0];
+        double v = (4. - x)*5.;
+        if (__double2hiint(x) < 0) { v = -v; } // std::signbit
+        out[0] = v;
+    }
+};
+
+} // namespace mcig_builtin

@@ -1,0 +1,393 @@
+// mcig_kernels.cuh — ahead-of-time sm_100a kernels of the engine that do not depend on user plugins:
+//   K2  combine_walkers      (replaces MPIMCI::integrate's reduce, src/MPIMCI.cpp:85-92)
+//   K4  est_uncorrelated     (MultiDim/OneDimUncorrelatedEstimator, src/Estimators.cpp:36-56, 125-155)
+//   K3  mj_segments + mj_finish (MJBlocker::estimate, src/MJBlocker.cpp:46-154) — one streaming read of the series
+//   K5  est_fcblocker        (FCBlockerEstimator, src/Estimators.cpp:82-122, 191-246) — single pass, 45 partitions at once
+//   finalize_simple / noop   (SimpleAccumulator::_finalize src/SimpleAccumulator.cpp:22-28, NoopEstimator :288-293)
+//   reduce_u64               (acceptance counters, src/MCIntegrator.cpp:587-592)
+//   dfma_peak / imad_peak    (issue-rate microbenchmarks: the FP64 roofline denominator, measured live by bench.py)
+//
+// Sample storage layout everywhere: data[(i*nobs + j)*W + w]  (store index i, observable component j, walker w):
+// a warp reads/writes 32 consecutive walkers = one 256 B segment.
+//
+// Estimator kernels avoid FMA contraction on purpose (explicit __dmul_rn/__dadd_rn): with one thread per chain they
+// then reproduce the reference's left-to-right sums bit for bit.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcig_k {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------------------------------------- small utilities
+__global__ void reduce_u64_kernel(const u64 * __restrict__ in, i64 n, u64 * __restrict__ out)
+{ // single block, deterministic
+    __shared__ u64 sm[32];
+    u64 s = 0;
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) { s += in[i]; }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); }
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = s; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); }
+        if (threadIdx.x == 0) { out[0] = s; }
+    }
+}
+
+// Simple accumulator finalize + Noop estimator: avg_w = sum_w * (1./NAccu), err_w = 0
+__global__ void finalize_simple_kernel(const double * __restrict__ sums, i64 n /*nobs*W*/, double normf, double * __restrict__ wavg,
+                                       double * __restrict__ werr)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) {
+        wavg[i] = __dmul_rn(sums[i], normf);
+        werr[i] = 0.;
+    }
+}
+
+// Noop estimator on stored data (Block/Full): "average" = first stored sample, error 0 (src/Estimators.cpp:288-293)
+__global__ void noop_first_kernel(const double * __restrict__ data, i64 n /*nobs*W*/, double * __restrict__ wavg, double * __restrict__ werr)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) {
+        wavg[i] = data[i];
+        werr[i] = 0.;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- K2 combine over walkers
+// out[3*nobsdim]: sum_w avg_w | sum_w err_w^2 | sum_w avg_w^2 . One block per observable component, fixed tree => deterministic.
+__global__ void combine_walkers_kernel(const double * __restrict__ wavg, const double * __restrict__ werr, i64 W, int nobsdim,
+                                       double * __restrict__ out)
+{
+    const int j = blockIdx.x;
+    __shared__ double sm[3][32];
+    double a = 0., e = 0., q = 0.;
+    for (i64 w = threadIdx.x; w < W; w += blockDim.x) {
+        const double v = wavg[(i64)j*W + w], r = werr[(i64)j*W + w];
+        a += v;
+        e += r*r;
+        q += v*v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        e += __shfl_down_sync(0xffffffffu, e, o);
+        q += __shfl_down_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sm[0][threadIdx.x >> 5] = a;
+        sm[1][threadIdx.x >> 5] = e;
+        sm[2][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const bool in = threadIdx.x < (blockDim.x >> 5);
+        a = in ? sm[0][threadIdx.x] : 0.;
+        e = in ? sm[1][threadIdx.x] : 0.;
+        q = in ? sm[2][threadIdx.x] : 0.;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            e += __shfl_down_sync(0xffffffffu, e, o);
+            q += __shfl_down_sync(0xffffffffu, q, o);
+        }
+        if (threadIdx.x == 0) {
+            out[j] = a;
+            out[nobsdim + j] = e;
+            out[2*nobsdim + j] = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- K4 uncorrelated estimator
+// Partial sums over a time segment: thread = (segment, column) with column = j*W + w. part[(seg*2 + {0,1})*ncol + col].
+__global__ void uncorr_partial_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nseg, double * __restrict__ part)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    const int seg = blockIdx.y;
+    if (col >= ncol) { return; }
+    const i64 i0 = n*seg/nseg, i1 = n*(seg + 1)/nseg;
+    double s = 0., q = 0.;
+    for (i64 i = i0; i < i1; ++i) {
+        const double v = __ldcs(data + i*ncol + col);
+        s = __dadd_rn(s, v);
+        q = __dadd_rn(q, __dmul_rn(v, v));
+    }
+    part[((i64)seg*2 + 0)*ncol + col] = s;
+    part[((i64)seg*2 + 1)*ncol + col] = q;
+}
+
+// nobs_is_one selects the 1-D formula sqrt(var/(n-1.)) vs the N-D one sqrt(var*(1./(n-1.))) (Estimators.cpp:49-50 vs :147-150)
+__global__ void uncorr_finish_kernel(const double * __restrict__ part, i64 n, i64 ncol, int nseg, int nobs_is_one, double * __restrict__ wavg,
+                                     double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    double s = 0., q = 0.;
+    for (int seg = 0; seg < nseg; ++seg) {
+        s = __dadd_rn(s, part[((i64)seg*2 + 0)*ncol + col]);
+        q = __dadd_rn(q, part[((i64)seg*2 + 1)*ncol + col]);
+    }
+    const double norm = 1./(double)n;
+    const double avg = __dmul_rn(s, norm);
+    double er = __dadd_rn(__dmul_rn(q, norm), -__dmul_rn(avg, avg));
+    if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/((double)n - 1.)) : sqrt(__dmul_rn(er, 1./((double)n - 1.))); }
+    else { er = 0.; }
+    wavg[col] = avg;
+    werr[col] = er;
+}
+
+// ---------------------------------------------------------------------------------------------- K3 MJBlocker
+// Streaming blocking pyramid over one aligned segment of L = 2^m samples of one chain (thread = (segment, column)).
+// For every level k < m it accumulates sum X^2 and sum X_i X_{i+1} inside the segment and remembers the first and
+// last centred element (for the products that straddle segment borders); the segment's level-m element (its mean)
+// goes to `top`. All levels come from ONE read of the series; the reference makes ~13 passes (src/MJBlocker.cpp:127-154).
+#define MCIG_MJ_MAXLEV 40
+struct MJLevel {
+    double pend;   // first element of an incomplete pair (uncentred)
+    double prevX;  // previous centred element of this level
+    double sq;     // sum X^2
+    double cr;     // sum X_i X_{i+1}
+    double firstX; // first centred element
+};
+
+__device__ __forceinline__ void mj_push(MJLevel * lv, unsigned long long & havemask, unsigned long long & cntmask, int m, double x0, double mean,
+                                        double & top)
+{ // insert one level-0 sample; carries propagate upwards like a binary counter
+    double x = x0;
+    for (int k = 0; k <= m; ++k) {
+        if (k == m) { top = x; return; }
+        const double X = __dadd_rn(x, -mean);
+        MJLevel & L = lv[k];
+        L.sq = __dadd_rn(L.sq, __dmul_rn(X, X));
+        if (havemask >> k & 1ULL) { L.cr = __dadd_rn(L.cr, __dmul_rn(L.prevX, X)); }
+        else { L.firstX = X; havemask |= 1ULL << k; }
+        L.prevX = X;
+        if (cntmask >> k & 1ULL) { // completes a pair
+            cntmask &= ~(1ULL << k);
+            x = __dmul_rn(0.5, __dadd_rn(L.pend, x));
+        }
+        else {
+            cntmask |= 1ULL << k;
+            L.pend = x;
+            return;
+        }
+    }
+}
+
+// seg_out layout: [(seg*m + k)*4 + {sq,cr,firstX,lastX}]*ncol + col ; top[seg*ncol + col]
+__global__ void mj_segments_kernel(const double * __restrict__ data, i64 ncol, i64 L, int m, const double * __restrict__ mean /*[ncol]*/,
+                                   double * __restrict__ seg_out, double * __restrict__ top)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    const i64 seg = blockIdx.y;
+    if (col >= ncol) { return; }
+    MJLevel lv[MCIG_MJ_MAXLEV];
+    for (int k = 0; k < m; ++k) { lv[k].sq = 0.; lv[k].cr = 0.; lv[k].firstX = 0.; lv[k].prevX = 0.; lv[k].pend = 0.; }
+    unsigned long long have = 0, cnt = 0;
+    const double mu = mean[col];
+    double t = 0.;
+    const double * src = data + seg*L*ncol + col;
+    for (i64 i = 0; i < L; ++i) { mj_push(lv, have, cnt, m, __ldcs(src + i*ncol), mu, t); }
+    for (int k = 0; k < m; ++k) {
+        double * o = seg_out + ((seg*m + k)*4)*ncol + col;
+        o[0] = lv[k].sq;
+        o[ncol] = lv[k].cr;
+        o[2*ncol] = lv[k].firstX;
+        o[3*ncol] = lv[k].prevX;
+    }
+    top[seg*ncol + col] = t;
+}
+
+__constant__ double c_mj_quantile[64] = {
+    3.841459, 5.991465, 7.814728, 9.487729, 11.070498, 12.591587, 14.067140, 15.507313, 16.918978, 18.307038, 19.675138,
+    21.026070, 22.362032, 23.684791, 24.995790, 26.296228, 27.587112, 28.869299, 30.143527, 31.410433, 32.670573, 33.924438,
+    35.172462, 36.415029, 37.652484, 38.885139, 40.113272, 41.337138, 42.556968, 43.772972, 44.985343, 46.194260, 47.399884,
+    48.602367, 49.801850, 50.998460, 52.192320, 53.383541, 54.572228, 55.758479, 56.942387, 58.124038, 59.303512, 60.480887,
+    61.656233, 62.829620, 64.001112, 65.170769, 66.338649, 67.504807, 68.669294, 69.832160, 70.993453, 72.153216, 73.311493,
+    74.468324, 75.623748, 76.777803, 77.930524, 79.081944, 80.232098, 81.381015, 82.528727, 83.675261};
+
+// One thread per chain: merges the per-segment statistics (levels < m), runs the pyramid over the nseg segment tops
+// (levels >= m), then the test statistic / level choice of src/MJBlocker.cpp:106-152.
+__global__ void mj_finish_kernel(const double * __restrict__ seg_out, const double * __restrict__ top, i64 ncol, i64 n, i64 nseg, int m, int npow,
+                                 const double * __restrict__ mean, double * __restrict__ wavg, double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    double var[MCIG_MJ_MAXLEV], gam[MCIG_MJ_MAXLEV];
+    const double mu = mean[col];
+    for (int k = 0; k < m; ++k) {
+        double sq = 0., cr = 0., lastX = 0.;
+        for (i64 s = 0; s < nseg; ++s) {
+            const double * o = seg_out + ((s*m + k)*4)*ncol + col;
+            if (s > 0) { cr = __dadd_rn(cr, __dmul_rn(lastX, o[2*ncol])); } // product across the segment border
+            sq = __dadd_rn(sq, o[0]);
+            cr = __dadd_rn(cr, o[ncol]);
+            lastX = o[3*ncol];
+        }
+        const double nred = (double)(n >> k);
+        var[k] = sq/nred;
+        gam[k] = cr/nred;
+    }
+    {
+        MJLevel lv[MCIG_MJ_MAXLEV];
+        const int mt = npow - m; // levels held by the tops
+        for (int k = 0; k < mt; ++k) { lv[k].sq = 0.; lv[k].cr = 0.; lv[k].firstX = 0.; lv[k].prevX = 0.; lv[k].pend = 0.; }
+        unsigned long long have = 0, cnt = 0;
+        double t = 0.;
+        for (i64 s = 0; s < nseg; ++s) { mj_push(lv, have, cnt, mt, top[s*ncol + col], mu, t); }
+        for (int k = 0; k < mt; ++k) {
+            const double nred = (double)(n >> (m + k));
+            var[m + k] = lv[k].sq/nred;
+            gam[m + k] = lv[k].cr/nred;
+        }
+    }
+    // _generateM + cumulative sums (src/MJBlocker.cpp:106-123)
+    double M[MCIG_MJ_MAXLEV];
+    for (int i = 0; i < npow; ++i) {
+        const double q = gam[i]/var[i];
+        M[npow - i - 1] = __dmul_rn(__dmul_rn(q, q), exp2((double)(npow - i)));
+    }
+    int kk = -1;
+    {
+        double Msum[MCIG_MJ_MAXLEV];
+        double run = 0.;
+        for (int i = 0; i < npow; ++i) {
+            run = __dadd_rn(run, M[i]);
+            Msum[i] = run;
+        }
+        for (kk = npow - 1; kk >= 0; --kk) {
+            if (Msum[kk] < c_mj_quantile[kk]) { break; }
+        }
+    }
+    const int k = npow - (kk + 1);
+    wavg[col] = mu;
+    // no level passes only when the variance is 0 (NaN statistics): the reference then reads out of bounds
+    // (SURVEY.md Appendix C #12); the error of a constant series is defined as 0 here
+    werr[col] = (k >= npow) ? 0. : sqrt(var[k]/exp2((double)(npow - k)));
+}
+
+// mean of stored data per column from the in-kernel running sums: mean = sum / n  (src/MJBlocker.cpp:46-55 divides)
+__global__ void mean_from_sum_kernel(const double * __restrict__ sums, i64 ncol, double n, double * __restrict__ mean)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col < ncol) { mean[col] = sums[col]/n; }
+}
+
+// ---------------------------------------------------------------------------------------------- K5 FCBlocker
+// One thread per chain, ONE pass over the series feeding all 45 block partitions (6..50 blocks) at once; block means are
+// pushed into the uncorrelated estimator's running sums in block order, so every sum has the reference's order.
+__device__ __forceinline__ double fc_err_delta(int mode, const double * e /*centre element*/)
+{ // calcErrDelta, src/Estimators.cpp:9-31
+    switch (mode) {
+    case 1: return (-0.5*e[-1] + 0.5*e[1]);
+    case 2: return ((1./12.)*e[-2] - (2./3.)*e[-1] + (2./3.)*e[1] - (1./12.)*e[2]);
+    case 3: return (-(1./60.)*e[-3] + (3./20.)*e[-2] - 0.75*e[-1] + 0.75*e[1] - (3./20.)*e[2] + (1./60.)*e[3]);
+    default:
+        return ((1./280.)*e[-4] - (4./105.)*e[-3] + 0.2*e[-2] - 0.8*e[-1] + 0.8*e[1] - 0.2*e[2] + (4./105.)*e[3] - (1./280.)*e[4]);
+    }
+}
+
+__global__ void fcblocker_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, double * __restrict__ wavg,
+                                 double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    constexpr int MINB = 6, MAXB = 50, NAV = MAXB - MINB + 1, MPA = 4, NACCD = NAV - 2*MPA;
+    double bsum[NAV], s1[NAV], s2[NAV];
+    int left[NAV];   // samples left in the current block
+    int bdone[NAV];  // completed blocks
+    for (int a = 0; a < NAV; ++a) {
+        bsum[a] = 0.; s1[a] = 0.; s2[a] = 0.;
+        left[a] = (int)(n/(a + MINB));
+        bdone[a] = 0;
+    }
+    for (i64 i = 0; i < n; ++i) {
+        const double v = __ldcs(data + i*ncol + col);
+        for (int a = 0; a < NAV; ++a) {
+            if (bdone[a] == a + MINB) { continue; } // remainder samples are ignored (Estimators.cpp:65, :164)
+            bsum[a] = __dadd_rn(bsum[a], v);
+            if (--left[a] == 0) {
+                const i64 nper = n/(a + MINB);
+                const double av = __dmul_rn(bsum[a], 1./(double)nper);
+                s1[a] = __dadd_rn(s1[a], av);
+                s2[a] = __dadd_rn(s2[a], __dmul_rn(av, av));
+                bsum[a] = 0.;
+                left[a] = (int)nper;
+                ++bdone[a];
+            }
+        }
+    }
+    double av[NAV], err[NAV];
+    for (int a = 0; a < NAV; ++a) {
+        const double nb = (double)(a + MINB);
+        const double norm = 1./nb;
+        const double mean = __dmul_rn(s1[a], norm);
+        double er = __dadd_rn(__dmul_rn(s2[a], norm), -__dmul_rn(mean, mean));
+        if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/(nb - 1.)) : sqrt(__dmul_rn(er, 1./(nb - 1.))); }
+        else { er = 0.; }
+        av[a] = mean;
+        err[a] = er;
+    }
+    double accd[NACCD];
+    for (int i2 = MPA; i2 < NACCD + MPA; ++i2) {
+        double acc = 0.;
+        for (int i1 = 1; i1 <= MPA; ++i1) { acc = __dadd_rn(acc, fc_err_delta(i1, err + i2)); }
+        accd[i2 - MPA] = acc;
+    }
+    int imin = 0;
+    for (int i2 = 1; i2 < NACCD; ++i2) {
+        if (fabs(accd[i2]) < fabs(accd[imin])) { imin = i2; }
+    }
+    imin += MPA;
+    wavg[col] = 0.2*(av[imin - 2] + av[imin - 1] + av[imin] + av[imin + 1] + av[imin + 2]);
+    werr[col] = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
+}
+
+// ---------------------------------------------------------------------------------------------- layout helpers
+// host-order [W][n] -> device-order [n][W] (replay draws, start positions)
+__global__ void transpose_kernel(const double * __restrict__ in, i64 W, i64 n, double * __restrict__ out)
+{
+    const i64 i = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < W*n) {
+        const i64 w = i%W, k = i/W;
+        out[i] = in[w*n + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- issue-rate microbenchmarks
+template <int ILP>
+__global__ void dfma_peak_kernel(double * out, int iters, double a, double b)
+{
+    double v[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) { v[j] = threadIdx.x*1e-9 + j; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) { v[j] = fma(v[j], a, b); }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) { s += v[j]; }
+    if (s == 123.456) { out[0] = s; }
+}
+
+template <int ILP>
+__global__ void imad_peak_kernel(unsigned * out, int iters, unsigned a, unsigned b)
+{
+    unsigned v[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) { v[j] = threadIdx.x + j; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) { v[j] = v[j]*a + b; }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) { s += v[j]; }
+    if (s == 0x12345678u) { out[0] = s; }
+}
+
+} // namespace mcig_k

@@ -1,0 +1,92 @@
+"""Named run configurations shared by oracle/gen_golden.py (which runs them through the UNMODIFIED reference and commits
+the outputs under tests/golden/) and by the parity tests. Each maps to keyword arguments of oracle/orc.py:make_config.
+
+Sources of the workloads (paths relative to the reference repository):
+  c1_*      BASELINE.json configs[0] pinned as SURVEY.md §8(d) C1 (3-D Gaussian / x^2, Simple, all-move)
+  mixed     benchmark/bench_integrate_mixed/main.cpp:28-46
+  tp3g      benchmark/bench_throughput_3G/main.cpp:23-38 (1-D Exp / X1D, Block(20), step 3.185) at a small Nmc
+  ut4_*     test/ut4/main.cpp:33-73   ut5_*  test/ut5/main.cpp:41-137   ut2_*  test/ut2/main.cpp:56-91
+  ndim_vec  benchmark/bench_throughput_ndim_single/main.cpp:26-50
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import orc  # noqa: E402
+
+
+def _alt(nd):
+    return [0.1 if j % 2 == 0 else -0.05 for j in range(nd)]
+
+
+RUNS = {
+    # --- all-move, 3-D Gaussian (the north-star integrand)
+    "c1_simple": dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=100000, steps=(1.0,)),
+    "c1_simple_short": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=4096, steps=(1.0,)),
+    "full_mj": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XYZSQUARED, 1, 1)], nmc=65536, steps=(1.0,)),
+    "full_fc": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XYZSQUARED, 1, 1)], nmc=60000, steps=(1.0,)),
+    "full_uncorr": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D,
+                        obs=[(orc.OBS_XSQUARED, 1, 1, True, orc.EST_UNCORRELATED), (orc.OBS_XYZSQUARED, 1, 1, True, orc.EST_UNCORRELATED)],
+                        nmc=65536, steps=(1.0,)),
+    "block16": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 16, 1), (orc.OBS_XYZSQUARED, 16, 1)], nmc=65536, steps=(1.0,)),
+    "block8_skip2_corr": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D,
+                              obs=[(orc.OBS_XSQUARED, 8, 2, True, orc.EST_CORRELATED), (orc.OBS_XYZSQUARED, 8, 2, True, orc.EST_CORRELATED)],
+                              nmc=65536, steps=(1.0,)),
+    "mixed": dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_XSQUARED, 1, 5), (orc.OBS_XYZSQUARED, 5, 2)],
+                  nmc=100000, steps=(1.0,)),
+    "tp3g_small": dict(ndim=1, seed=1337, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 20, 1)], nmc=100000, steps=(3.185,)),
+    # --- automatic calibration + decorrelation
+    "auto_default": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=65536, x0=(5., -5., 10.), do_find=True, do_decorr=True),
+    "ut2_irange": dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=10000, x0=(5., -5., 10.), lb=-5., ub=5.,
+                       do_find=True, do_decorr=True),
+    "ut4_fixed": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XYZSQUARED, 16, 1)], nmc=16384,
+                      x0=(5., -5., 10.), nfind=20, ndecorr=2000, do_find=True, do_decorr=True),
+    "ut3_two_obs": dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XYZSQUARED, 1, 1)], nmc=10000,
+                        x0=(5., -5., 10.), do_find=True, do_decorr=True),
+    # --- single-vector moves / typed step sizes / selective updates
+    "vec_exp4": dict(ndim=4, seed=1337, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 0, 1)], nmc=50000, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,), x0=_alt(4)),
+    "vec_gauss3_auto": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 3), (orc.OBS_X2, 1, 3)], nmc=32768*3, move_type=orc.MOVE_VEC,
+                            veclen=1, do_find=True, do_decorr=True),
+    "vec3_types": dict(ndim=6, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 2), (orc.OBS_UPDXND, 4, 1)], nmc=32768, move_type=orc.MOVE_VEC, veclen=3,
+                       ntypes=2, type_ends=[3, 6], steps=(0.4, 0.8), do_find=True, do_decorr=True),
+    "all_types": dict(ndim=4, seed=77, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1), (orc.OBS_POLYNOM, 0, 1)], nmc=16384, ntypes=2, type_ends=[1, 4],
+                      steps=(0.9, 0.5)),
+    "ndim_vec16": dict(ndim=16, seed=1337, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 0, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,),
+                       x0=_alt(16), ndecorr=2000, do_decorr=True),
+    "ndim_all16": dict(ndim=16, seed=1337, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 0, 1)], nmc=20000, steps=(0.4,), x0=_alt(16)),
+    "ndim_all64": dict(ndim=64, seed=4242, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 8, 1)], nmc=8192, steps=(0.12,), x0=_alt(64)),
+    "ndim_vec64_v4": dict(ndim=64, seed=4242, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 4), (orc.OBS_XND, 0, 1)], nmc=16384, move_type=orc.MOVE_VEC,
+                          veclen=4, steps=(0.6,), x0=_alt(64)),
+    # --- MultiStepMove
+    "ms_default4": dict(ndim=4, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1)], nmc=50000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.7,)),
+    "ms_sub_ut5": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_X2, 1, 3)], nmc=32768*3, move_type=orc.MOVE_MULTISTEP,
+                       veclen=1, ms_nsteps=3, ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.1,), do_find=True, do_decorr=True, target_acc=0.85),
+    "ms_sub16": dict(ndim=16, seed=99, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 20, 1)], nmc=4000, move_type=orc.MOVE_MULTISTEP, veclen=1,
+                     ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.5,), x0=_alt(16)),
+    "ms_nosub8": dict(ndim=8, seed=5, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=4000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.3,),
+                      x0=_alt(8)),
+    # --- no sampling function (plain MC over a box), ex_basic
+    "nopdf_box": dict(ndim=3, seed=42, pdf_id=orc.PDF_NONE, obs=[(orc.OBS_GAUSSXSQUARED, 1, 1)], nmc=16384, lb=-5., ub=5.),
+    "exbasic_1": dict(ndim=1, seed=7, pdf_id=orc.PDF_NONE, obs=[(orc.OBS_PARABOLA, 1, 1)], nmc=100000, lb=-1., ub=3., x0=(-0.5,), steps=(0.25,), target_acc=0.7,
+                      do_find=True, do_decorr=True),
+    "exbasic_2": dict(ndim=1, seed=7, pdf_id=orc.PDF_NORMLINE, obs=[(orc.OBS_NORMPARABOLA, 1, 1)], nmc=100000, lb=-1., ub=3., x0=(-0.5,), steps=(0.25,),
+                      target_acc=0.7, do_find=True, do_decorr=True),
+}
+
+
+def make(name):
+    kw = dict(RUNS[name])
+    ndim, seed, pdf_id, obs, nmc = kw.pop("ndim"), kw.pop("seed"), kw.pop("pdf_id"), kw.pop("obs"), kw.pop("nmc")
+    return orc.make_config(ndim, seed, pdf_id, obs, nmc, **kw)
+
+
+# TestWalk data sets for estimator parity: (pdf 0 SLATER / 1 GAUSS, nmc, ndim, step, change_prob, srand seed)
+# bench_estimators (benchmark/bench_estimators/main.cpp:31-51) at reduced size, ut1 (test/ut1/main.cpp:228-230)
+WALKS = {
+    "ut1_gauss": (1, 32768, 2, 2.0, 0.5, 1337),
+    "est_1d": (0, 65536, 1, 1.59, 1.0, 1337),
+    "est_16d": (0, 4096, 16, 0.313, 1.0, 1337),
+    "est_1d_npow2": (0, 60000, 1, 1.59, 1.0, 4711),
+    "est_3d_npow2": (1, 50001, 3, 0.8, 1.0, 99),
+    "est_small": (0, 346, 3, 0.8, 1.0, 5),
+}

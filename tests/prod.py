@@ -1,0 +1,52 @@
+"""Build a product MCI (CUDA path through the C-ABI) from the same keyword spec the oracle configs use (tests/configs.py)."""
+import orc
+
+PDF_NAMES = {orc.PDF_GAUSS3D: "ThreeDimGaussianPDF", orc.PDF_GAUSS: "Gauss", orc.PDF_EXP1D: "Exp1DPDF", orc.PDF_EXPND: "ExpNDPDF",
+             orc.PDF_NORMLINE: "NormalizedLine"}
+OBS_NAMES = {orc.OBS_XSQUARED: "XSquared", orc.OBS_GAUSSXSQUARED: "GaussXSquared", orc.OBS_XYZSQUARED: "XYZSquared", orc.OBS_X1D: "X1D",
+             orc.OBS_XND: "XND", orc.OBS_UPDXND: "UpdateableXND", orc.OBS_CONSTVAL: "Constval", orc.OBS_POLYNOM: "Polynom",
+             orc.OBS_X2SUM: "X2Sum", orc.OBS_X2: "X2", orc.OBS_PARABOLA: "Parabola", orc.OBS_NORMPARABOLA: "NormalizedParabola"}
+
+
+def build_mci(m, spec, nwalkers=1, mode=None, seeds=None, placement=None):
+    kw = dict(spec)
+    ndim = kw["ndim"]
+    mci = m.MCI(ndim)
+    mci.setRngMode(m.RngMode.Replay if mode is None else mode)
+    if nwalkers != 1:
+        mci.setNWalkers(nwalkers)
+    mci.setSeed(kw["seed"])
+    if seeds is not None:
+        mci.setWalkerSeeds(seeds)
+    if kw.get("lb") is not None:
+        mci.setIRange(kw["lb"], kw["ub"])
+    mt = kw.get("move_type", orc.MOVE_ALL)
+    ntypes = kw.get("ntypes", 1)
+    te = kw.get("type_ends")
+    if mt == orc.MOVE_ALL:
+        mci.setTrialMove(m.SRRDType.Uniform, 0, ntypes, te)
+    elif mt == orc.MOVE_VEC:
+        mci.setTrialMove(m.SRRDType.Uniform, max(1, kw.get("veclen", 1)), ntypes, te)
+    else:
+        sub = []
+        if kw.get("ms_sub_pdf_id", 0):
+            sub.append(m.SamplingFunction(PDF_NAMES[kw["ms_sub_pdf_id"]]))
+        mci.setTrialMove(m.MoveType.MultiStep, max(1, kw.get("veclen", 1)), ntypes, te, nsteps=kw.get("ms_nsteps", 0), sub_pdfs=sub)
+    steps = list(kw.get("steps", (0.05,)))
+    for i in range(max(1, ntypes)):
+        mci.setMRT2Step(i, steps[i] if i < len(steps) else steps[-1])
+    mci.setX(kw.get("x0") if kw.get("x0") is not None else [0.0]*ndim)
+    if kw["pdf_id"]:
+        mci.addSamplingFunction(m.SamplingFunction(PDF_NAMES[kw["pdf_id"]]))
+    for o in kw["obs"]:
+        o = tuple(o)
+        bs, ns = max(0, o[1]), max(1, o[2])
+        fe = o[3] if len(o) > 3 else bs > 0
+        et = o[4] if len(o) > 4 else orc.default_estim(bs)
+        mci.addObservable(m.Observable(OBS_NAMES[o[0]]), bs, ns, fe, m.EstimatorType(et))
+    mci.setTargetAcceptanceRate(kw.get("target_acc", 0.5))
+    mci.setNfindMRT2Iterations(kw.get("nfind", -50))
+    mci.setNdecorrelationSteps(kw.get("ndecorr", -10000))
+    if placement is not None:
+        mci.setStatePlacement(placement)
+    return mci

@@ -1,0 +1,98 @@
+"""CPU: the C-ABI library loads, exports every symbol include/mcig.h declares, generates and JIT-compiles (NVRTC needs no
+GPU) the walk kernel for the headline configurations, and fails LOUDLY — no CPU fallback — when asked to compute."""
+import os
+import re
+
+import pytest
+
+import configs
+from prod import build_mci
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(mcig):
+    hdr = open(os.path.join(ROOT, "include", "mcig.h")).read()
+    declared = set(re.findall(r"\b(mcig_[a-z0-9_]+)\s*\(", hdr)) - {"mcig_allreduce_fn"}
+    from mcintegratorplusplus_b200 import _capi
+    lib = _capi.lib()
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libmcig.so does not export %s" % name
+    assert declared == set(_capi.SIGNATURES), "ctypes table out of sync with include/mcig.h"
+    assert lib.mcig_version() == 100
+
+
+def test_builtin_plugins_registered(mcig):
+    from mcintegratorplusplus_b200 import _capi
+    lib = _capi.lib()
+    for n in ("ThreeDimGaussianPDF", "Gauss", "Exp1DPDF", "ExpNDPDF", "NormalizedLine"):
+        assert lib.mcig_lookup_plugin(0, n.encode()) >= 0
+    for n in ("XSquared", "GaussXSquared", "XYZSquared", "X1D", "XND", "UpdateableXND", "Constval", "Polynom", "X2Sum", "X2", "Parabola",
+              "NormalizedParabola"):
+        assert lib.mcig_lookup_plugin(1, n.encode()) >= 0
+    assert lib.mcig_lookup_plugin(0, b"nope") == -1
+
+
+@pytest.mark.parametrize("name", ["c1_simple", "mixed", "vec_exp4", "ndim_vec16", "ms_sub_ut5", "ms_sub16", "nopdf_box", "ut2_irange", "vec3_types",
+                                  "ndim_all64", "ndim_vec64_v4"])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_jit_compiles_without_gpu(name, mode, mcig, tmp_path, monkeypatch):
+    monkeypatch.setenv("MCIG_CACHE_DIR", str(tmp_path))
+    mci = build_mci(mcig, configs.RUNS[name], mode=mode)
+    src = mci.kernelSource()
+    assert "mcig_walk" in src and "struct Glue" in src
+    mci.prebuild()
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
+
+
+def test_user_plugin_source_compiles(mcig, tmp_path, monkeypatch):
+    monkeypatch.setenv("MCIG_CACHE_DIR", str(tmp_path))
+    src = """
+struct MyQuartic { // exp(-(a*sum x^4)), a = par[0]
+    static constexpr int NPAR = 1; static constexpr bool HAS_UPDATE = false; static constexpr bool ELEMENTWISE = false;
+    const double * par;
+    template <class X, class P> __device__ void protoFunction(const X & in, P & pv) const { double s = 0.; for (int i = 0; i < 2; ++i) { const double q = in[i]*in[i]; s += q*q; } pv[0] = par[0]*s; }
+    template <class P> __device__ double samplingFunction(const P & pv) const { return mcig::exp(-pv[0]); }
+    template <class PO, class PN> __device__ double acceptanceFunction(const PO & po, const PN & pn) const { return mcig::exp(po[0] - pn[0]); }
+};
+"""
+    mcig.register_plugin(0, "MyQuartic", "MyQuartic", src, ndim=2, nvalues=1, npar=1)
+    mci = mcig.MCI(2)
+    mci.addSamplingFunction(mcig.SamplingFunction("MyQuartic", par=[0.5]))
+    mci.addObservable(mcig.X2Sum(2), 16, 1)
+    mci.prebuild()
+    assert "MyQuartic" in mci.kernelSource()
+
+
+def test_argument_errors_mirror_reference(mcig):
+    from mcintegratorplusplus_b200._capi import McigError
+    mci = mcig.MCI(3)
+    with pytest.raises(McigError, match="number of inputs is not equal"):
+        mci.addSamplingFunction(mcig.Exp1DPDF())  # 1-D pdf into a 3-D MCI: src/MCIntegrator.cpp:486-488
+    with pytest.raises(McigError, match="number of inputs is not equal"):
+        mci.addObservable(mcig.X1D())  # src/MCIntegrator.cpp:456-458
+    with pytest.raises(McigError, match="requires estimator with error calculation"):
+        mci.addObservable(mcig.XSquared(), 1, 1, True, mcig.EstimatorType.Noop)  # src/MCIntegrator.cpp:459-461
+    with pytest.raises(McigError, match="multiple of passed veclen"):
+        mci.setTrialMove(mcig.SRRDType.Uniform, 2)  # src/MCIntegrator.cpp:435-437
+    with pytest.raises(McigError, match="truly greater"):
+        mci.setIRange(1.0, -1.0)  # src/OrthoPeriodicDomain.cpp:6-13
+    with pytest.raises(McigError, match="infinite domain"):
+        mci.addObservable(mcig.XSquared())
+        mci.integrate(100)  # no pdf, unbound domain: src/MCIntegrator.cpp:45-47
+
+
+def test_no_cpu_fallback(mcig):
+    """Without a GPU every compute entry point must raise, never silently compute on the host."""
+    from mcintegratorplusplus_b200 import _capi
+    if _capi.lib().mcig_device_count() > 0:
+        pytest.skip("a GPU is present")
+    mci = build_mci(mcig, configs.RUNS["c1_simple_short"], mode=0)
+    with pytest.raises(_capi.McigError, match="no CUDA device"):
+        mci.integrate(128, False, False)
+    import numpy as np
+    with pytest.raises(_capi.McigError, match="no CUDA device"):
+        mcig.estimate(mcig.EstimatorType.Uncorrelated, np.arange(64.))
+    with pytest.raises(_capi.McigError, match="no CUDA device"):
+        mcig.measure_peaks()

@@ -1,0 +1,61 @@
+"""GPU: device estimators (K3 MJBlocker, K4 uncorrelated, K5 FCBlocker, Noop) through mcig_estimate against the C oracle and
+the reference's golden values, on the reference's own TestWalk data (test/ut1, benchmark/bench_estimators)."""
+import numpy as np
+import pytest
+
+import configs
+import orc
+from conftest import fromhex
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("wname", sorted(configs.WALKS))
+def test_estimators_match_reference(wname, mcig, oracle, golden_est):
+    pdf, nmc, ndim, step, cp, seed = configs.WALKS[wname]
+    datax, _, _, _, _ = oracle.testwalk(pdf, nmc, ndim, step, cp, seed)
+    x = datax if ndim > 1 else datax[:, 0]
+    g = golden_est[wname]
+    for ename, et in (("uncorrelated", orc.EST_UNCORRELATED), ("correlated", orc.EST_CORRELATED), ("fcblocker", orc.EST_FCBLOCKER),
+                      ("mjblocker", orc.EST_MJBLOCKER), ("noop", orc.EST_NOOP)):
+        if ename not in g:
+            continue
+        avg, err = mcig.estimate(et, x)
+        ga, ge = np.array(fromhex(g[ename]["avg"])), np.array(fromhex(g[ename]["err"]))
+        assert np.allclose(avg, ga, rtol=1e-12, atol=1e-15), (ename, avg, ga)
+        assert np.allclose(err, ge, rtol=1e-9, atol=1e-18), (ename, err, ge)
+
+
+def test_mjblocker_large_power_of_two_segments(mcig, oracle):
+    """A series long enough to be time-split into segments (the HBM-streaming path) against the oracle's 13-pass algorithm."""
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    e = rng.normal(size=(n, 2))
+    x = np.empty_like(e)
+    x[0] = e[0]
+    for i in range(1, n):  # AR(1) correlated series
+        x[i] = 0.9*x[i - 1] + e[i]
+    avg_o, err_o = oracle.estimate(orc.EST_MJBLOCKER, x)
+    avg, err = mcig.estimate(orc.EST_MJBLOCKER, x)
+    assert np.allclose(avg, avg_o, rtol=1e-12, atol=1e-15)
+    assert np.allclose(err, err_o, rtol=1e-9)
+    avg_u, err_u = mcig.estimate(orc.EST_UNCORRELATED, x)
+    avg_uo, err_uo = oracle.estimate(orc.EST_UNCORRELATED, x)
+    assert np.allclose(avg_u, avg_uo, rtol=1e-12, atol=1e-15) and np.allclose(err_u, err_uo, rtol=1e-9)
+    assert np.all(err > 2*err_u)  # blocking must see the correlation
+
+
+def test_constant_series_defined_error(mcig):
+    """Constval-like data: the reference reads out of bounds; here err is defined as 0."""
+    avg, err = mcig.estimate(orc.EST_MJBLOCKER, np.full(1024, 1.3))
+    assert avg[0] == pytest.approx(1.3, rel=1e-15) and err[0] == 0.0
+
+
+def test_estimator_argument_errors(mcig):
+    from mcintegratorplusplus_b200._capi import McigError
+    with pytest.raises(McigError, match="power of two"):
+        mcig.estimate(orc.EST_MJBLOCKER, np.arange(100.))
+    with pytest.raises(McigError, match=">= 50"):
+        mcig.estimate(orc.EST_FCBLOCKER, np.arange(40.))
+    with pytest.raises(McigError, match="larger than 1"):
+        mcig.estimate(orc.EST_UNCORRELATED, np.arange(1.))

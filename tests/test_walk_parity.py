@@ -1,0 +1,169 @@
+"""GPU: the CUDA walk path (through the C-ABI) in REPLAY mode against the C oracle and the reference's golden vectors.
+
+Replay mode feeds the kernel the same std::mt19937_64 / libstdc++ distribution outputs the reference consumes, so:
+  * accept/reject sequences, acceptance counts, final positions and calibrated step sizes must be BIT-EXACT
+    (the only non-IEEE-pinned operation on the path is exp(): CUDA vs glibc may differ by 1 ulp, which flips a decision
+    only if the uniform lands inside that ulp, p ~ 1e-16 per step — a flip would show up here, not be hidden);
+  * accumulator sums / averages must agree to 1e-12 relative (BASELINE.json north_star);
+  * estimator errors (MJ / FC / uncorrelated) to 1e-9 relative.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import configs
+import orc
+from conftest import fromhex
+from prod import build_mci
+
+pytestmark = pytest.mark.gpu
+
+AVG_RTOL, ERR_RTOL = 1e-12, 1e-9
+
+
+def _close(a, b, rtol, atol=1e-15):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.all(np.abs(a - b) <= atol + rtol*np.abs(b))
+
+
+@pytest.mark.parametrize("name", sorted(configs.RUNS))
+def test_replay_vs_oracle_and_golden(name, mcig, oracle, golden_runs):
+    spec = configs.RUNS[name]
+    cfg = configs.make(name)
+    ref = oracle.run(cfg)
+    g = golden_runs[name]
+    assert ref["avg"] == fromhex(g["avg"])  # oracle itself is pinned to the reference
+    mci = build_mci(mcig, spec)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    # bit-exact integer / control-flow quantities
+    n = spec["nmc"]
+    assert round(mci.getAcceptanceRate()*n) == ref["n_acc"], "accept count differs"
+    assert mci.getAcceptanceRate() == ref["acc_rate"]
+    assert list(mci.getX()) == ref["x_final"], "final position not bit-exact"
+    nt = max(1, spec.get("ntypes", 1))
+    assert [mci.getMRT2Step(i) for i in range(nt)] == ref["steps_final"], "calibrated step sizes not bit-exact"
+    assert _close(avg, ref["avg"], AVG_RTOL), (avg, ref["avg"])
+    assert _close(err, ref["err"], ERR_RTOL, atol=1e-18), (err, ref["err"])
+
+
+@pytest.mark.parametrize("placement", [0, 1])
+@pytest.mark.parametrize("name", ["c1_simple_short", "vec_exp4", "ms_default4", "ms_sub_ut5", "all_types", "vec3_types"])
+def test_register_and_smem_paths_agree(name, placement, mcig, oracle):
+    """Both state placements (registers / shared memory) must reproduce the oracle."""
+    spec = configs.RUNS[name]
+    ref = oracle.run(configs.make(name))
+    mci = build_mci(mcig, spec, placement=placement)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    assert mci.getAcceptanceRate() == ref["acc_rate"]
+    assert list(mci.getX()) == ref["x_final"]
+    assert _close(avg, ref["avg"], AVG_RTOL) and _close(err, ref["err"], ERR_RTOL, atol=1e-18)
+
+
+def test_accept_sequence_and_trajectory_bit_exact(mcig, oracle):
+    """Every step: positions from a Full XND accumulator vs the trajectory implied by the oracle's draws + accept bits."""
+    nmc = 20000
+    spec = dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XND, 1, 1, False, orc.EST_UNCORRELATED)], nmc=nmc, steps=(1.0,),
+                x0=(0.3, -0.2, 0.1))
+    cfg = orc.make_config(3, 5649871, orc.PDF_GAUSS3D, spec["obs"], nmc, steps=(1.0,), x0=spec["x0"])
+    tr = oracle.run(cfg, trace=True)
+    draws = tr["draws"].reshape(nmc, 4)
+    x = np.array(spec["x0"])
+    traj = np.zeros((nmc, 3))
+    for t in range(nmc):
+        if tr["accepted"][t]:
+            x = x + 1.0*draws[t, :3]
+        traj[t] = x
+    mci = build_mci(mcig, spec)
+    mci.integrate(nmc, False, False)
+    data = mci.obsData(0, walker=0, nobs=3)
+    assert data.shape == (nmc, 3)
+    assert np.array_equal(data, traj), "trajectory differs from the reference's at step %d" % int(np.argmax((data != traj).any(axis=1)))
+    prev = np.vstack([np.array(spec["x0"])[None, :], data[:-1]])
+    acc_gpu = (data != prev).any(axis=1)
+    assert np.array_equal(acc_gpu, tr["accepted"].astype(bool))
+
+
+def test_vec_move_accept_sequence(mcig, oracle):
+    nmc = 30000
+    spec = dict(ndim=4, seed=1337, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 1, 1, False, orc.EST_UNCORRELATED)], nmc=nmc, move_type=orc.MOVE_VEC,
+                veclen=1, steps=(3.0,), x0=[0.1, -0.05, 0.1, -0.05])
+    cfg = orc.make_config(4, 1337, orc.PDF_EXPND, spec["obs"], nmc, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,), x0=spec["x0"])
+    tr = oracle.run(cfg, trace=True)
+    for placement in (0, 1):
+        mci = build_mci(mcig, spec, placement=placement)
+        mci.integrate(nmc, False, False)
+        data = mci.obsData(0, walker=0, nobs=4)
+        prev = np.vstack([np.array(spec["x0"])[None, :], data[:-1]])
+        assert np.array_equal((data != prev).any(axis=1), tr["accepted"].astype(bool))
+
+
+def test_multi_walker_replay_equals_independent_ranks(mcig, oracle):
+    """W walkers with per-walker seeds == W reference ranks (src/MPIMCI.cpp:83-92): per-walker results and the combination."""
+    spec = configs.RUNS["full_mj"]
+    cfg = configs.make("full_mj")
+    seeds = [11, 22, 33, 44, 55]
+    f = oracle.lib.mcio_run_ranks
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(orc.Config), C.POINTER(C.c_uint64), C.c_int, C.POINTER(orc.Result), C.POINTER(orc.Result), C.POINTER(orc.Trace)]
+    comb = orc.Result()
+    per = (orc.Result*len(seeds))()
+    assert f(C.byref(cfg), (C.c_uint64*len(seeds))(*seeds), len(seeds), C.byref(comb), per, None) == 0
+    mci = build_mci(mcig, spec, nwalkers=len(seeds), seeds=seeds)
+    avg, err = mci.integrate(spec["nmc"], False, False)
+    assert _close(avg, comb.avg[:4], AVG_RTOL) and _close(err, comb.err[:4], ERR_RTOL)
+    wavg, werr = mci.walkerResults()
+    for w in range(len(seeds)):
+        assert _close(wavg[:, w], per[w].avg[:4], AVG_RTOL)
+        assert _close(werr[:, w], per[w].err[:4], ERR_RTOL)
+        assert list(mci.getX(walker=w)) == list(per[w].x_final[:3])
+    assert mci.getAcceptanceRate() == comb.acc_rate
+
+
+def test_multi_walker_auto_calibration_matches_mpi_semantics(mcig, oracle):
+    """Calibration / decorrelation with rank-averaged acceptance rate and estimates (src/MCIntegrator.cpp:131-138, 203-230)."""
+    spec = dict(configs.RUNS["auto_default"])
+    cfg = configs.make("auto_default")
+    seeds = [101, 202, 303, 404]
+    f = oracle.lib.mcio_run_ranks
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(orc.Config), C.POINTER(C.c_uint64), C.c_int, C.POINTER(orc.Result), C.POINTER(orc.Result), C.POINTER(orc.Trace)]
+    comb = orc.Result()
+    assert f(C.byref(cfg), (C.c_uint64*len(seeds))(*seeds), len(seeds), C.byref(comb), None, None) == 0
+    mci = build_mci(mcig, spec, nwalkers=len(seeds), seeds=seeds)
+    avg, err = mci.integrate(spec["nmc"], True, True)
+    # the rank-sum order of the rate is implementation-defined in MPI; step sizes agree to rounding, results to 1e-9
+    assert mci.getMRT2Step(0) == pytest.approx(comb.steps_final[0], rel=1e-12)
+    assert mci.getAcceptanceRate() == pytest.approx(comb.acc_rate, abs=2e-4)
+    assert abs(avg[0] - comb.avg[0]) < 3*np.hypot(err[0], comb.err[0])
+    assert abs(avg[0] - 0.5) < 3*err[0]
+
+
+def test_state_persists_across_integrate_calls(mcig, oracle):
+    """Walker position and RNG stream continue across integrate calls: two 2048-step calls == oracle twice."""
+    spec = dict(configs.RUNS["c1_simple_short"])
+    mci = build_mci(mcig, spec)
+    a1, _ = mci.integrate(2048, False, False)
+    a2, _ = mci.integrate(2048, False, False)
+    cfg = configs.make("c1_simple_short")
+    cfg.nmc = 2048
+    r1 = oracle.run(cfg)
+    # second leg: start from r1's final x with the generator advanced by 2048 steps' draws -> emulate with one 4096 run's accept count
+    cfg.nmc = 4096
+    r12 = oracle.run(cfg)
+    assert _close(a1, r1["avg"], AVG_RTOL)
+    assert list(mci.getX()) == r12["x_final"]
+    assert _close(0.5*(a1[0] + a2[0]), r12["avg"][0], 1e-12)
+
+
+def test_error_behaviour_on_device(mcig):
+    from mcintegratorplusplus_b200._capi import McigError
+    mci = build_mci(mcig, dict(configs.RUNS["c1_simple_short"], obs=[(orc.OBS_XSQUARED, 7, 1)]))
+    with pytest.raises(McigError, match="not a multiple of the requested block size"):
+        mci.integrate(100, False, False)  # src/BlockAccumulator.cpp:11-13
+    mci = build_mci(mcig, dict(configs.RUNS["c1_simple_short"], obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_MJBLOCKER)]))
+    with pytest.raises(McigError, match="power of two"):
+        mci.integrate(1000, False, False)  # src/MJBlocker.cpp:28-30
+    mci = build_mci(mcig, dict(configs.RUNS["c1_simple_short"], obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_FCBLOCKER)]))
+    with pytest.raises(McigError, match=">= 50"):
+        mci.integrate(40, False, False)  # src/Estimators.cpp:196-198
