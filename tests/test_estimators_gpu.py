@@ -45,10 +45,15 @@ def test_mjblocker_large_power_of_two_segments(mcig, oracle):
     assert np.all(err > 2*err_u)  # blocking must see the correlation
 
 
-def test_constant_series_defined_error(mcig):
-    """Constval-like data: the reference reads out of bounds (SURVEY.md Appendix C #12); here err is defined as 0."""
+def test_constant_series_defined_error(mcig, oracle):
+    """Constval-like data (test/main.cpp:82-88). An exactly representable constant has zero variance at every level: the
+    reference then reads out of bounds; here and in the oracle err is defined as 0. A constant
+    like 1.3 leaves rounding residue in x - mean and behaves like ordinary data: compare with the oracle."""
+    avg, err = mcig.estimate(orc.EST_MJBLOCKER, np.full(1024, 1.5))
+    assert avg[0] == 1.5 and err[0] == 0.0
     avg, err = mcig.estimate(orc.EST_MJBLOCKER, np.full(1024, 1.3))
-    assert avg[0] == pytest.approx(1.3, rel=1e-15) and err[0] == 0.0
+    avg_o, err_o = oracle.estimate(orc.EST_MJBLOCKER, np.full(1024, 1.3))
+    assert avg[0] == avg_o[0] and err[0] == pytest.approx(err_o[0], rel=1e-9, abs=1e-18)
 
 
 def test_estimator_argument_errors(mcig):

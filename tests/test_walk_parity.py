@@ -125,6 +125,7 @@ def test_multi_walker_auto_calibration_matches_mpi_semantics(mcig, oracle):
     spec = dict(configs.RUNS["auto_default"])
     cfg = configs.make("auto_default")
     seeds = [101, 202, 303, 404]
+    cfg.nranks_for_minstat = len(seeds)  # MIN_STAT / MIN_NMC shrink with the number of ranks: src/MCIntegrator.cpp:107, :193
     f = oracle.lib.mcio_run_ranks
     f.restype = C.c_int
     f.argtypes = [C.POINTER(orc.Config), C.POINTER(C.c_uint64), C.c_int, C.POINTER(orc.Result), C.POINTER(orc.Result), C.POINTER(orc.Trace)]

@@ -1,0 +1,23 @@
+"""Short run of the headline walk kernel for ncu (one launch is replayed ~40x under --set full: keep it small)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mcintegratorplusplus_b200 as m  # noqa: E402
+
+nmc = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+bs = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+mci = m.MCI(3)
+mci.setRngMode(0)
+mci.setSeed(1337)
+mci.setNWalkers(W)
+mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+mci.addObservable(m.XSquared(), 0, 1)
+mci.setMRT2Step(1.0)
+if bs:
+    mci.setBlockSize(bs)
+for _ in range(3):
+    avg, err = mci.integrate(nmc, False, False)
+t = mci.timings()
+print("W=%d nmc=%d bs=%d walk %.3f ms -> %.4e steps/s, avg %.6f acc %.4f" % (W, nmc, bs, t["walk_ms"], W*nmc/(t["walk_ms"]*1e-3), avg[0], mci.getAcceptanceRate()))
