@@ -37,35 +37,55 @@ METRIC = "metropolis_samples_per_sec"
 WORKLOAD = "bench_throughput_3G: ThreeDimGaussianPDF ndim=3 + XSquared, uniform all-move step 1.0, SimpleAccumulator, 65536 walkers/GPU x 1e5 steps"
 
 
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region: one streaming `nvidia-smi -lms 100` child (B200_PROFILING.md)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.stop_flag = False
-        self.max_mhz = None
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(n)
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
 
-    def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s)//2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line))
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        mhz, reasons, mx, pw = [], set(), None, []
+        for t, line in self.lines:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                mhz.append(float(f[0]))
+                mx = float(f[1])
+                pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(self.NAMES, f[3:]):
+                if v.startswith("Active"):
+                    reasons.add(n)
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz)//2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz),
+                "power_w_max": max(pw) if pw else None}
 
 
 def make_mci(m, rank, world):
@@ -186,7 +206,7 @@ def main():
     for _ in range(max(3, args.warmup)):
         mci.integrate(NMC, False, False)
     sampler = ClockSampler(local)
-    sampler.start()
+    time.sleep(0.3)
     barrier()
     t0 = time.perf_counter()
     dev_ms, walk_ms, launches = 0.0, 0.0, 0
@@ -198,9 +218,11 @@ def main():
         walk_ms += tm["walk_ms"]
         launches += tm["launches"]
     barrier()
-    wall_ms = 1e3*(time.perf_counter() - t0)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    t1 = time.perf_counter()
+    wall_ms = 1e3*(t1 - t0)
+    time.sleep(0.15)
+    sampler.stop()
+    clocks = sampler.summary(t0, t1)
     dev_ms = maxreduce(dev_ms)
     wall_ms = maxreduce(wall_ms)
     walk_ms_max = maxreduce(walk_ms)
@@ -243,7 +265,7 @@ def main():
                          "achieved_tflops": FLOP_PER_STEP*steps_per_s_kernel/1e12, "peak_tflops": 2*peaks[0]/1e12,
                          "peak_source": "DFMA/s measured live by mcig_measure_peaks on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                          "imad_peak_ginst": peaks[1]/1e9},
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "result": {"avg": float(avg[0]), "err": float(err[0]), "acceptance": float(rate), "cross_walker_err_local": float(mci.crossWalkerError()[0])},
         }
         if not args.no_cpu_baseline and world >= 1:

@@ -1,0 +1,2 @@
+// MultiStepMove lives in TrialMoveInterface.hpp (header kept for source compatibility with the reference include list)
+#include "mci/TrialMoveInterface.hpp"

@@ -1,0 +1,178 @@
+// Trial moves — mirror of include/mci/TrialMoveInterface.hpp:16-70, TypedMoveInterface.hpp:20-63, SRRDAllMove.hpp,
+// SRRDVecMove.hpp, MultiStepMove.hpp. The proposal itself runs in the walk kernel (device/mcig_device.cuh, MOVE 0/1/2);
+// these host objects carry the move's configuration (kind, vector length, typed step sizes, MultiStep sub-move and
+// sub-sampling functions) and the step-size accessors findMRT2Step needs. Only the uniform distribution has a device
+// sampler so far: the other SRRDType enumerators are accepted by the factories and rejected by MCI.
+#ifndef MCIG_MCI_TRIALMOVEINTERFACE_HPP
+#define MCIG_MCI_TRIALMOVEINTERFACE_HPP
+
+#include "mci/Clonable.hpp"
+#include "mci/SamplingFunctionInterface.hpp"
+
+#include <algorithm>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+namespace mci
+{
+enum class MoveType { All, Vec, MultiStep };                  // include/mci/Factories.hpp:108-114
+enum class SRRDType { Uniform, Gaussian, Student, Cauchy, Exponential, Gamma, Weibull, Lognormal, Chisq, Fisher }; // :119-133
+static constexpr double DEFAULT_MRT2STEP = 0.05;              // include/mci/Factories.hpp:145
+
+class TrialMoveInterface: public Clonable<TrialMoveInterface>
+{
+protected:
+    const int _ndim;
+    explicit TrialMoveInterface(int ndim): _ndim(ndim) {}
+
+public:
+    int getNDim() const { return _ndim; }
+    bool hasStepSizes() const { return this->getNStepSizes() > 0; }
+    virtual MoveType getMoveType() const = 0;
+    virtual SRRDType getSRRDType() const { return SRRDType::Uniform; }
+    virtual int getVecLen() const { return 1; }
+    virtual int getNTypes() const = 0;
+    virtual const int * getTypeEnds() const = 0;
+    virtual int getNStepSizes() const = 0;
+    virtual double getStepSize(int i) const = 0;
+    virtual void setStepSize(int i, double val) = 0;
+    virtual double getChangeRate() const = 0;
+    virtual int getStepSizeIndex(int xidx) const = 0;
+    void scaleStepSize(int i, double fac) { this->setStepSize(i, this->getStepSize(i)*fac); }
+    void scaleStepSizes(double fac)
+    {
+        for (int i = 0; i < this->getNStepSizes(); ++i) { this->scaleStepSize(i, fac); }
+    }
+};
+
+// typed step sizes: x = (a0,a1,a2,b0,b1,c0) -> ntypes 3, typeEnds (3,5,6)
+class TypedMoveInterface: public TrialMoveInterface
+{
+protected:
+    const int _ntypes;
+    std::vector<int> _typeEnds;
+    std::vector<double> _stepSizes;
+    const SRRDType _srrd;
+    TypedMoveInterface(int ndim, int ntypes, const int typeEnds[], double initStepSize, SRRDType srrd):
+            TrialMoveInterface(ndim), _ntypes(ntypes), _srrd(srrd)
+    {
+        if (_ntypes < 1) { throw std::invalid_argument("[TypedMoveInterface] Number of types must be at least 1."); }
+        if (_ntypes > 1) {
+            if (typeEnds == nullptr) { throw std::invalid_argument("[TypedMoveInterface] When ntypes>1, passed typeEnds must not be null."); }
+            _typeEnds.assign(typeEnds, typeEnds + _ntypes);
+        }
+        else { _typeEnds.assign(1, ndim); }
+        _stepSizes.assign(static_cast<size_t>(_ntypes), initStepSize);
+    }
+
+public:
+    SRRDType getSRRDType() const final { return _srrd; }
+    int getNTypes() const final { return _ntypes; }
+    const int * getTypeEnds() const final { return _typeEnds.data(); }
+    int getNStepSizes() const final { return _ntypes; }
+    void setStepSize(int i, double val) final { _stepSizes[static_cast<size_t>(i)] = val; }
+    double getStepSize(int i) const final { return _stepSizes[static_cast<size_t>(i)]; }
+    int getStepSizeIndex(int xidx) const final
+    {
+        for (int i = 0; i < _ntypes; ++i) {
+            if (xidx < _typeEnds[static_cast<size_t>(i)]) { return i; }
+        }
+        throw std::runtime_error("[TypedMoveInterface::getUsedStepSize] Passed xidx exceeds expected range.");
+    }
+};
+
+// all-particle move with a symmetric real-valued random distribution (include/mci/SRRDAllMove.hpp)
+class SRRDAllMove final: public TypedMoveInterface
+{
+    TrialMoveInterface * _clone() const final { return new SRRDAllMove(*this); }
+
+public:
+    SRRDAllMove(int ndim, int ntypes, const int typeEnds[], double initStepSize, SRRDType srrd = SRRDType::Uniform):
+            TypedMoveInterface(ndim, ntypes, typeEnds, initStepSize, srrd) {}
+    SRRDAllMove(int ndim, double initStepSize, SRRDType srrd = SRRDType::Uniform): SRRDAllMove(ndim, 1, nullptr, initStepSize, srrd) {}
+    MoveType getMoveType() const final { return MoveType::All; }
+    double getChangeRate() const final { return 1.; }
+};
+
+// single-vector move (include/mci/SRRDVecMove.hpp)
+class SRRDVecMove final: public TypedMoveInterface
+{
+    const int _nvecs, _veclen;
+    TrialMoveInterface * _clone() const final { return new SRRDVecMove(*this); }
+
+public:
+    SRRDVecMove(int nvecs, int veclen, int ntypes, const int typeEnds[], double initStepSize, SRRDType srrd = SRRDType::Uniform):
+            TypedMoveInterface(nvecs*veclen, ntypes, typeEnds, initStepSize, srrd), _nvecs(nvecs), _veclen(veclen)
+    {
+        if (_nvecs < 1) { throw std::invalid_argument("[SRRDVecMove] Number of vectors must be at least 1."); }
+        if (_veclen < 1) { throw std::invalid_argument("[SRRDVecMove] Vector length must be at least 1."); }
+        if (_ntypes > 1) {
+            for (int e : _typeEnds) {
+                if (e%_veclen != 0) { throw std::invalid_argument("[SRRDVecMove] All type end indices must be multiples of vector length."); }
+            }
+        }
+    }
+    SRRDVecMove(int nvecs, int veclen, double initStepSize, SRRDType srrd = SRRDType::Uniform): SRRDVecMove(nvecs, veclen, 1, nullptr, initStepSize, srrd) {}
+    MoveType getMoveType() const final { return MoveType::Vec; }
+    int getVecLen() const final { return _veclen; }
+    double getChangeRate() const final { return 1./_nvecs; }
+};
+
+// names of the reference's uniform instantiations (include/mci/SRRDAllMove.hpp:84, SRRDVecMove.hpp:100): the distribution is a
+// run-time tag here (default uniform), so UniformAllMove(ndim, step) / UniformVecMove(nvecs, veclen, step) construct as in the reference
+using UniformAllMove = SRRDAllMove;
+using UniformVecMove = SRRDVecMove;
+
+// MultiStepMove (include/mci/MultiStepMove.hpp:21-84, src/MultiStepMove.cpp:6-47): mini-Metropolis of nsteps sub-moves driven by
+// the move's own sampling functions; default sub-move = uniform single-index move with step 0.05, default nsteps = ndim.
+class MultiStepMove final: public TrialMoveInterface
+{
+    int _nsteps;
+    std::unique_ptr<TrialMoveInterface> _trialMove;
+    std::vector<std::unique_ptr<SamplingFunctionInterface>> _pdfs;
+    TrialMoveInterface * _clone() const final
+    {
+        auto * ret = new MultiStepMove(_ndim, _nsteps);
+        ret->setTrialMove(*_trialMove);
+        for (auto & p : _pdfs) { ret->addSamplingFunction(*p); }
+        return ret;
+    }
+
+public:
+    MultiStepMove(int ndim, int nsteps): TrialMoveInterface(ndim), _nsteps(nsteps), _trialMove(new SRRDVecMove(ndim, 1, DEFAULT_MRT2STEP)) {}
+    explicit MultiStepMove(int ndim): MultiStepMove(ndim, ndim) {}
+    void setNSteps(int nsteps) { _nsteps = nsteps; }
+    void setTrialMove(const TrialMoveInterface & tmove)
+    {
+        if (tmove.getNDim() != _ndim) {
+            throw std::invalid_argument("[MultiStepMove::setTrialMove] Passed trial move's number of inputs is not equal to number of walkers.");
+        }
+        if (tmove.getMoveType() != MoveType::Vec) { throw std::domain_error("[MultiStepMove::setTrialMove] the device engine supports single-vector sub-moves only"); }
+        _trialMove = tmove.clone();
+    }
+    void addSamplingFunction(const SamplingFunctionInterface & pdf)
+    {
+        if (pdf.getNDim() != _ndim) {
+            throw std::invalid_argument("[MultiStepMove::addSamplingFunction] Passed sampling function's number of inputs is not equal to number of walkers.");
+        }
+        _pdfs.emplace_back(pdf.clone());
+    }
+    void clearSamplingFunctions() { _pdfs.clear(); }
+    int getNSteps() const { return _nsteps; }
+    TrialMoveInterface & getTrialMove() const { return *_trialMove; }
+    int getNPDF() const { return static_cast<int>(_pdfs.size()); }
+    SamplingFunctionInterface & getSamplingFunction(int i) const { return *_pdfs[static_cast<size_t>(i)]; }
+
+    MoveType getMoveType() const final { return MoveType::MultiStep; }
+    int getVecLen() const final { return _trialMove->getVecLen(); }
+    int getNTypes() const final { return _trialMove->getNTypes(); }
+    const int * getTypeEnds() const final { return _trialMove->getTypeEnds(); }
+    int getNStepSizes() const final { return _trialMove->getNStepSizes(); }
+    double getStepSize(int i) const final { return _trialMove->getStepSize(i); }
+    void setStepSize(int i, double val) final { _trialMove->setStepSize(i, val); }
+    double getChangeRate() const final { return std::min(1., _trialMove->getChangeRate()*_nsteps); }
+    int getStepSizeIndex(int xidx) const final { return _trialMove->getStepSizeIndex(xidx); }
+};
+} // namespace mci
+#endif

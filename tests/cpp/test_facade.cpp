@@ -1,0 +1,164 @@
+// C++ facade test, written like the reference's own unit tests (test/ut2/main.cpp, test/ut4/main.cpp, test/ut5/main.cpp):
+// plain asserts on 2-3 sigma agreement with known expectations, plus API behaviour (ownership, exceptions, getters).
+// argv[1] == "api": only the checks that need no GPU.
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "mci/DeviceFunctions.hpp"
+#include "mci/Estimators.hpp"
+#include "mci/MCIntegrator.hpp"
+#include "mci/MPIMCI.hpp"
+
+using namespace mci;
+
+template <class E, class F>
+static bool throws(F f)
+{
+    try { f(); }
+    catch (const E &) { return true; }
+    catch (...) { return false; }
+    return false;
+}
+
+static void test_api()
+{
+    MCI mci(3);
+    assert(mci.getNDim() == 3 && mci.getNObs() == 0 && mci.getNPDF() == 0);
+    assert(mci.getTargetAcceptanceRate() == 0.5 && mci.getNfindMRT2Iterations() == -50 && mci.getNdecorrelationSteps() == -10000);
+    assert(mci.getMRT2Step(0) == 0.05 && mci.getMRT2Step(1) == 0.); // DEFAULT_MRT2STEP, out-of-range index -> 0
+    assert(!mci.getDomain().isFinite());
+    // setters / getters (test/ut2/main.cpp:20-54)
+    double x[3] = {5., -5., 10.};
+    mci.setX(x);
+    assert(mci.getX(0) == 5. && mci.getX(1) == -5. && mci.getX(2) == 10.);
+    mci.setX(1, 2.5);
+    assert(mci.getX(1) == 2.5);
+    mci.setIRange(-1., 1.); // periodic wrap of the current position
+    assert(mci.getDomain().isFinite() && mci.getDomain().getVolume() == 8.);
+    for (int i = 0; i < 3; ++i) { assert(mci.getX(i) >= -1. && mci.getX(i) <= 1.); }
+    mci.newRandomX();
+    for (int i = 0; i < 3; ++i) { assert(mci.getX(i) >= -1. && mci.getX(i) <= 1.); }
+    auto olddom = mci.resetDomain();
+    assert(olddom->isFinite() && !mci.getDomain().isFinite());
+    // ownership: set*/pop* hand the previous object back
+    auto oldmove = mci.setTrialMove(MoveType::Vec);
+    assert(oldmove->getMoveType() == MoveType::All && mci.getTrialMove().getChangeRate() == 1./3.);
+    int typeEnds[2] = {1, 3};
+    mci.setTrialMove(SRRDType::Uniform, 0, 2, typeEnds);
+    assert(mci.getTrialMove().getNStepSizes() == 2 && mci.getTrialMove().getStepSizeIndex(0) == 0 && mci.getTrialMove().getStepSizeIndex(2) == 1);
+    double steps[2] = {0.3, 0.6};
+    mci.setMRT2Step(steps);
+    assert(mci.getMRT2Step(1) == 0.6);
+    mci.addSamplingFunction(ThreeDimGaussianPDF());
+    mci.addObservable(XSquared());
+    mci.addObservable(XYZSquared(), 16, 1);
+    assert(mci.getNObs() == 2 && mci.getNObsDim() == 4 && mci.getNPDF() == 1);
+    auto popped = mci.popObservable();
+    assert(popped->getNObs() == 3 && mci.getNObsDim() == 1);
+    // exceptions
+    assert(throws<std::invalid_argument>([&] { mci.addSamplingFunction(Exp1DPDF()); }));
+    assert(throws<std::invalid_argument>([&] { mci.addObservable(X1D()); }));
+    assert(throws<std::invalid_argument>([&] { mci.addObservable(XSquared(), 1, 1, true, EstimatorType::Noop); }));
+    assert(throws<std::invalid_argument>([&] { mci.setTrialMove(SRRDType::Uniform, 2); }));
+    assert(throws<std::invalid_argument>([&] { mci.setIRange(1., -1.); }));
+    assert(throws<std::invalid_argument>([&] { mci.setDomain(OrthoPeriodicDomain(2, -1., 1.)); }));
+    assert(throws<std::domain_error>([&] { mci.setTrialMove(SRRDType::Gaussian); }));
+    assert(throws<std::invalid_argument>([] { selectEstimatorType(true, false); }));
+    MultiStepMove msm(3);
+    assert(msm.getNSteps() == 3 && msm.getChangeRate() == 1.);
+    assert(throws<std::invalid_argument>([&] { msm.addSamplingFunction(Exp1DPDF()); }));
+    std::cout << "api ok" << std::endl;
+}
+
+static void test_gpu()
+{
+    double avg[4], err[4];
+    { // test/ut2/main.cpp:56-91 — bad start needs the warm-up; with calibration + decorrelation the result is right
+        MCI mci(3);
+        mci.setSeed(5649871);
+        mci.setNWalkers(256);
+        double x[3] = {5., -5., 10.};
+        mci.setX(x);
+        mci.addSamplingFunction(ThreeDimGaussianPDF());
+        mci.addObservable(XSquared());
+        mci.integrate(10000, avg, err, false, false);
+        assert(fabs(avg[0] - 0.5) > 2.*err[0]); // no warm-up from (5,-5,10): biased
+        mci.setX(x);
+        mci.setMRT2Step(0.05);
+        mci.integrate(10000, avg, err, true, true);
+        assert(fabs(avg[0] - 0.5) < 3.*err[0]);
+        assert(fabs(mci.getAcceptanceRate() - 0.5) < 0.05 && mci.getMRT2Step(0) > 0.5);
+        // no sampling function over a box (test/ut2/main.cpp:94-108)
+        mci.clearSamplingFunctions();
+        mci.clearObservables();
+        mci.addObservable(GaussXSquared());
+        mci.setIRange(-5., 5.);
+        mci.integrate(10000, avg, err);
+        assert(fabs(avg[0] - 0.5) < 3.*err[0]);
+        assert(throws<std::domain_error>([&] { mci.resetDomain(); mci.integrate(100, avg, err); }));
+    }
+    { // test/ut4/main.cpp:33-73 — fixed calibration/decorrelation, MJBlocker on 16384 samples, fixed blocks
+        MCI mci(3);
+        mci.setSeed(1337);
+        mci.setNWalkers(128);
+        mci.setNfindMRT2Iterations(20);
+        mci.setNdecorrelationSteps(2000);
+        mci.addSamplingFunction(ThreeDimGaussianPDF());
+        mci.addObservable(XSquared(), 1, 1);
+        mci.addObservable(XYZSquared(), 16, 1);
+        mci.integrate(16384, avg, err);
+        for (int i = 0; i < 4; ++i) { assert(err[i] > 0. && fabs(avg[i] - 0.5) < 3.5*err[i]); }
+        assert(throws<std::invalid_argument>([&] { mci.integrate(1000, avg, err, false, false); })); // 1000 % 16 != 0
+    }
+    { // test/ut5/main.cpp:113-137 — custom MultiStepMove with sub-move UniformVecMove and sub-pdf ExpNDPDF, target 0.85
+        MCI mci(3);
+        mci.setSeed(1337);
+        mci.setNWalkers(128);
+        MultiStepMove msm(3, 3);
+        msm.setTrialMove(UniformVecMove(3, 1, 0.1));
+        msm.addSamplingFunction(ExpNDPDF(3));
+        mci.setTrialMove(msm);
+        mci.setTargetAcceptanceRate(0.85);
+        mci.addSamplingFunction(Gauss(3));
+        mci.addObservable(XSquared());
+        mci.addObservable(X2(3), 1, 3);
+        mci.integrate(32768, avg, err);
+        for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
+        assert(fabs(mci.getAcceptanceRate() - 0.85) < 0.06);
+    }
+    { // replay mode, 1 walker: bit-exact reference numbers (generated from the compiled reference)
+        MCI mci(3);
+        mci.setRngMode(RngMode::Replay);
+        mci.setSeed(5649871);
+        mci.addSamplingFunction(ThreeDimGaussianPDF());
+        mci.addObservable(XSquared(), 0, 1);
+        mci.setMRT2Step(1.0);
+        mci.integrate(100000, avg, err, false, false);
+        assert(fabs(avg[0] - 0.49129926481208264) < 1e-12*0.5);
+        assert(mci.getAcceptanceRate() == 0.50334);
+        assert(mci.getX(0) == 0.56622698245761904 && mci.getX(2) == 0.65777044965711584);
+    }
+    { // free estimator functions on host data
+        std::vector<double> x(4096);
+        for (size_t i = 0; i < x.size(); ++i) { x[i] = sin(0.37*static_cast<double>(i)) + 0.001*static_cast<double>(i % 7); }
+        double a1, e1, a2[1], e2[1];
+        OneDimUncorrelatedEstimator(4096, x.data(), a1, e1);
+        MJBlockerEstimator(4096, 1, x.data(), a2, e2);
+        assert(fabs(a1 - a2[0]) < 1e-14 && e1 > 0. && e2[0] > 0.);
+        assert(throws<std::invalid_argument>([&] { MJBlockerEstimator(1000, 1, x.data(), a2, e2); }));
+    }
+    std::cout << "gpu ok" << std::endl;
+}
+
+int main(int argc, char ** argv)
+{
+    test_api();
+    if (argc > 1 && strcmp(argv[1], "api") == 0) { return 0; }
+    test_gpu();
+    return 0;
+}
