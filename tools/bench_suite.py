@@ -1,0 +1,102 @@
+"""Secondary workloads of BASELINE.json (configs[2..4], pinned in SURVEY.md §8(d) C3/C4/C5) on one GPU: one JSON line each.
+Not the driver's bench (that is bench.py, C2); these numbers go to profiles/ and DESIGN.md."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import mcintegratorplusplus_b200 as m  # noqa: E402
+
+HBM_GBS = 6550.7  # MEASURED_PEAKS.json (driver-measured copy bandwidth on this pool)
+
+
+def c3_ndim(move, ndims=(1, 2, 4, 8, 16, 32, 64), W=65536, nmc=20000):
+    for nd in ndims:
+        mci = m.MCI(nd)
+        mci.setRngMode(0)
+        mci.setSeed(1337)
+        mci.setNWalkers(W)
+        if move == "vec":
+            mci.setTrialMove(m.MoveType.Vec)
+        elif move == "multistep":
+            mci.setTrialMove(m.MoveType.MultiStep, 1, sub_pdfs=[m.ExpNDPDF(nd)] if nd > 1 else [])
+        else:
+            mci.setTrialMove(m.MoveType.All)
+        mci.setX([0.1 if j % 2 == 0 else -0.05 for j in range(nd)])
+        mci.setMRT2Step(3.0 if move == "vec" else (0.5 if move == "multistep" else 3.0/np.sqrt(nd)))
+        mci.addSamplingFunction(m.ExpNDPDF(nd) if move != "multistep" else m.Gauss(nd))
+        mci.addObservable(m.XND(nd), 20, 1)  # BlockAccumulator(20) + Uncorrelated
+        mci.integrate(2000, False, False)
+        t0 = time.perf_counter()
+        avg, err = mci.integrate(nmc, False, False)
+        wall = time.perf_counter() - t0
+        t = mci.timings()
+        print(json.dumps({"config": "C3_ndim_" + move, "ndim": nd, "walkers": W, "nmc": nmc, "steps_per_s": W*nmc/(t["walk_ms"]*1e-3),
+                          "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "wall_ms": 1e3*wall, "acceptance": mci.getAcceptanceRate(),
+                          "max_abs_avg": float(np.max(np.abs(avg))), "max_err": float(np.max(err))}), flush=True)
+
+
+def c4_estimators(W=65536, npow=14):
+    nmc = 1 << npow
+    for label, est in (("MJBlocker", m.EstimatorType.MJBlocker), ("Uncorrelated", m.EstimatorType.Uncorrelated), ("FCBlocker", m.EstimatorType.FCBlocker)):
+        mci = m.MCI(3)
+        mci.setRngMode(0)
+        mci.setSeed(1337)
+        mci.setNWalkers(W)
+        mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+        mci.addObservable(m.XSquared(), 1, 1, False, est)  # FullAccumulator
+        mci.setMRT2Step(1.0)
+        mci.integrate(nmc, False, False)
+        avg, err = mci.integrate(nmc, False, False)
+        t = mci.timings()
+        nbytes = 8.0*nmc*W
+        print(json.dumps({"config": "C4_estimators", "estimator": label, "walkers": W, "n_per_chain": nmc, "series_GB": nbytes/1e9,
+                          "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "estim_GBps": nbytes/(t["estim_ms"]*1e-3)/1e9,
+                          "hbm_frac_of_measured": nbytes/(t["estim_ms"]*1e-3)/1e9/HBM_GBS, "walk_steps_per_s": W*nmc/(t["walk_ms"]*1e-3),
+                          "walk_store_GBps": nbytes/(t["walk_ms"]*1e-3)/1e9, "avg": float(avg[0]), "err": float(err[0])}), flush=True)
+    # one long chain block, n = 2^27 (BASELINE "Nmc=1e8 per chain block" -> next power of two), host data through mcig_estimate
+    rng = np.random.default_rng(1)
+    n = 1 << 27
+    x = rng.normal(size=n)
+    for i in range(0, 3):
+        t0 = time.perf_counter()
+        avg, err = m.estimate(m.EstimatorType.MJBlocker, x)
+        wall = time.perf_counter() - t0
+    print(json.dumps({"config": "C4_single_chain_2^27", "estimator": "MJBlocker", "wall_ms_incl_1GiB_H2D": 1e3*wall, "avg": float(avg[0]), "err": float(err[0]),
+                      "expected_err": float(1/np.sqrt(n))}), flush=True)
+
+
+def c5_mixed(W=65536, nmc=100000):
+    mci = m.MCI(3)
+    mci.setRngMode(0)
+    mci.setSeed(5649871)
+    mci.setNWalkers(W)
+    mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+    mci.addObservable(m.XND(3), 0, 1)
+    mci.addObservable(m.XSquared(), 1, 5)
+    mci.addObservable(m.XYZSquared(), 5, 2)
+    mci.setMRT2Step(1.0)
+    for auto in (False, True):
+        mci.integrate(1000, False, False)
+        t0 = time.perf_counter()
+        avg, err = mci.integrate(nmc, auto, auto)
+        wall = time.perf_counter() - t0
+        t = mci.timings()
+        print(json.dumps({"config": "C5_mixed", "auto_calibration_decorrelation": auto, "walkers": W, "nmc": nmc, "samples_per_s_total": W*nmc/(t["total_ms"]*1e-3),
+                          "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "total_ms": t["total_ms"], "wall_ms": 1e3*wall, "launches": t["launches"],
+                          "step": mci.getMRT2Step(0), "acceptance": mci.getAcceptanceRate(), "avg": [float(v) for v in avg], "err": [float(v) for v in err]}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c3", "c4", "c5"]
+    if "c3" in which:
+        c3_ndim("vec")
+        c3_ndim("all")
+        c3_ndim("multistep", ndims=(2, 4, 8, 16, 32))
+    if "c4" in which:
+        c4_estimators()
+    if "c5" in which:
+        c5_mixed()
