@@ -39,18 +39,19 @@ struct DeviceFunctor
     std::vector<double> params; // run-time parameters (functor member `par`)
     bool hasUpdate = false;     // functor overrides updatedAcceptance
     bool elementwise = false;   // proto value k depends on x[k] only
+    bool logAcceptance = false; // functor provides logAcceptance(protoold, protonew)
 
     DeviceFunctor() = default;
     explicit DeviceFunctor(std::string registeredName, std::vector<double> par = {}): name(std::move(registeredName)), params(std::move(par)) {}
-    DeviceFunctor(std::string n, std::string type, std::string src, std::vector<double> par = {}, bool upd = false, bool elem = false):
-            name(std::move(n)), typeExpr(std::move(type)), source(std::move(src)), params(std::move(par)), hasUpdate(upd), elementwise(elem) {}
+    DeviceFunctor(std::string n, std::string type, std::string src, std::vector<double> par = {}, bool upd = false, bool elem = false, bool logacc = false):
+            name(std::move(n)), typeExpr(std::move(type)), source(std::move(src)), params(std::move(par)), hasUpdate(upd), elementwise(elem), logAcceptance(logacc) {}
 
     // returns the plugin id, registering the functor first if it brings its own source
     int resolve(int kind, int ndim, int nvalues) const
     {
         if (!typeExpr.empty()) {
-            const int id = mcig_register_plugin(kind, name.c_str(), typeExpr.c_str(), source.c_str(), ndim, nvalues, static_cast<int>(params.size()),
-                                                hasUpdate ? 1 : 0, elementwise ? 1 : 0);
+            const int flags = (hasUpdate ? MCIG_PLUGIN_HAS_UPDATE : 0) | (elementwise ? MCIG_PLUGIN_ELEMENTWISE : 0) | (logAcceptance ? MCIG_PLUGIN_LOG_ACCEPTANCE : 0);
+            const int id = mcig_register_plugin(kind, name.c_str(), typeExpr.c_str(), source.c_str(), ndim, nvalues, static_cast<int>(params.size()), flags);
             if (id < 0) { detail::check(-id); }
             return id;
         }

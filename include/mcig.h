@@ -44,6 +44,12 @@ enum {
                               the kernel in the reference's order: bit-exact reference trajectories (parity mode) */
 };
 enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1 };
+/* plugin flags (sampling functions) */
+enum {
+    MCIG_PLUGIN_HAS_UPDATE = 1,     /* functor overrides updatedAcceptance (selective update for single-vector moves) */
+    MCIG_PLUGIN_ELEMENTWISE = 2,    /* proto value k depends on x[k] only; updatedAcceptance touches protonew[changedIdx] only */
+    MCIG_PLUGIN_LOG_ACCEPTANCE = 4  /* functor provides logAcceptance(protoold, protonew) = log(acceptanceFunction) */
+};
 
 const char * mcig_last_error(void);
 int mcig_version(void);
@@ -54,9 +60,10 @@ int mcig_device_count(void);
  *      (include/mci/SamplingFunctionInterface.hpp:36-105, ObservableFunctionInterface.hpp:30-63) re-expressed as
  *      __device__ functors. `source` is CUDA C++ pasted into the JIT translation unit (may be NULL for built-ins),
  *      `type_expr` the functor type with "{ndim}" substituted (e.g. "mcig_builtin::Gauss<{ndim}>").
- *      ndim == 0: any dimension; nvalues == 0: nproto / nobs equals ndim. Returns the plugin id (>= 0) or -1. */
+ *      ndim == 0: any dimension; nvalues == 0: nproto / nobs equals ndim; flags: MCIG_PLUGIN_* bits.
+ *      Returns the plugin id (>= 0) or -(error code). */
 int mcig_register_plugin(int kind, const char * name, const char * type_expr, const char * source, int ndim, int nvalues,
-                         int npar, int has_update, int elementwise);
+                         int npar, int flags);
 /* id of a registered plugin (the reference's fixtures are pre-registered under their class names), or -1 */
 int mcig_lookup_plugin(int kind, const char * name);
 

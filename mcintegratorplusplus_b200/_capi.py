@@ -20,7 +20,7 @@ SIGNATURES = {
     "mcig_last_error": (C.c_char_p, []),
     "mcig_version": (C.c_int, []),
     "mcig_device_count": (C.c_int, []),
-    "mcig_register_plugin": (C.c_int, [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mcig_register_plugin": (C.c_int, [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mcig_lookup_plugin": (C.c_int, [C.c_int, C.c_char_p]),
     "mcig_create": (_ctx, [C.c_int]),
     "mcig_destroy": (None, [_ctx]),

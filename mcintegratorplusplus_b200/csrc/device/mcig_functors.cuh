@@ -13,6 +13,9 @@
 //       template <class P> __device__ double samplingFunction(const P & pv) const;
 //       template <class PO, class PN> __device__ double acceptanceFunction(const PO & po, const PN & pn) const;
 //       template <class W, class PO, class PN> __device__ double updatedAcceptance(const W & wlk, const PO & po, PN & pn) const;
+//       // optional (registration flag MCIG_PLUGIN_LOG_ACCEPTANCE): log of acceptanceFunction. When every sampling function
+//       // of an integrator provides it, production modes test u <= exp(sum of logs) with an FP32 pre-filter (accept_log).
+//       template <class PO, class PN> __device__ double logAcceptance(const PO & po, const PN & pn) const;
 //   };
 //   struct MyObs {                                  // mirrors mci::ObservableFunctionInterface
 //       static constexpr int NPAR = 0;
@@ -45,6 +48,8 @@ struct ThreeDimGaussianPDF { // TestMCIFunctions.hpp:123-148 (ndim 3, nproto 1)
     MCIG_DEV double samplingFunction(const P & pv) const { return exp(-pv[0]); }
     template <class PO, class PN>
     MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const { return exp(-pn[0] + po[0]); }
+    template <class PO, class PN>
+    MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const { return -pn[0] + po[0]; }
 };
 
 template <int NDIM>
@@ -77,6 +82,16 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return exp(a - b);
     }
+    template <class PO, class PN>
+    MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const
+    {
+        double a = 0., b = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { a += po[i]; }
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
+        return a - b;
+    }
     template <class W, class PO, class PN>
     MCIG_DEV double updatedAcceptance(const W & wlk, const PO & po, PN & pn) const
     {
@@ -103,6 +118,8 @@ struct Exp1DPDF { // TestMCIFunctions.hpp:189-215
     MCIG_DEV double samplingFunction(const P & pv) const { return exp(-pv[0]); }
     template <class PO, class PN>
     MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const { return exp(-pn[0] + po[0]); }
+    template <class PO, class PN>
+    MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const { return -pn[0] + po[0]; }
 };
 
 template <int NDIM>
@@ -134,6 +151,16 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
 #pragma unroll
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return exp(a - b);
+    }
+    template <class PO, class PN>
+    MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const
+    {
+        double a = 0., b = 0.;
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { a += po[i]; }
+#pragma unroll
+        for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
+        return a - b;
     }
     template <class W, class PO, class PN>
     MCIG_DEV double updatedAcceptance(const W & wlk, const PO & po, PN & pn) const

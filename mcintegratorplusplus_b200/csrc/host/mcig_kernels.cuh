@@ -468,6 +468,7 @@ __global__ void fcblocker_events_kernel(const double * __restrict__ data, i64 n,
             ++e;
             next = (e < nev) ? ev_pos[e] : n + 1;
         }
+        if (e >= nev) { break; } // the remainder after the last block border is ignored by every partition (Estimators.cpp:65, :164)
     }
     double av[NAV], err[NAV];
     for (int a = 0; a < NAV; ++a) {

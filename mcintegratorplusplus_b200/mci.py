@@ -73,10 +73,10 @@ class Observable(Plugin):
     kind = 1
 
 
-def register_plugin(kind, name, type_expr, source, ndim=0, nvalues=0, npar=0, has_update=False, elementwise=False):
+def register_plugin(kind, name, type_expr, source, ndim=0, nvalues=0, npar=0, has_update=False, elementwise=False, log_acceptance=False):
     """Register a user functor (CUDA C++ source, see csrc/device/mcig_functors.cuh for the contract)."""
-    pid = _capi.lib().mcig_register_plugin(kind, name.encode(), type_expr.encode(), (source or "").encode(), ndim, nvalues, npar,
-                                           int(has_update), int(elementwise))
+    flags = (1 if has_update else 0) | (2 if elementwise else 0) | (4 if log_acceptance else 0)
+    pid = _capi.lib().mcig_register_plugin(kind, name.encode(), type_expr.encode(), (source or "").encode(), ndim, nvalues, npar, flags)
     if pid < 0:
         raise _capi.McigError(-pid, _capi.lib().mcig_last_error().decode())
     return pid

@@ -85,3 +85,22 @@ def test_symmetric_expectations_exact(name, exact, mcig):
     avg, _ = mci.integrate(4000, False, False)
     cw = mci.crossWalkerError()
     assert np.all(np.abs(avg - exact) < 4.5*cw + 1e-12), (avg, cw)
+
+
+def test_fp32_prefilter_never_changes_a_decision(mcig, monkeypatch):
+    """The FP32 pre-filter of the accept test (device/mcig_device.cuh:accept_log) must give exactly the decisions of the plain
+    FP64 test u <= exp(d): same seed, same streams => bit-identical per-walker averages, positions and acceptance counts."""
+    spec = dict(ndim=3, seed=2024, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=20000, steps=(1.0,), x0=(0.3, -0.1, 0.2))
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_ACCEPT_PREFILTER=" + flag)
+        for mode in (0, 1):
+            mci = build_mci(mcig, spec, nwalkers=4096, mode=mode)
+            assert ("MCIG_ACCEPT_PREFILTER " + flag) in mci.kernelSource()
+            mci.integrate(20000, False, False)
+            wavg, _ = mci.walkerResults()
+            res.append((flag, mode, wavg.copy(), mci.getAcceptanceRate(), np.array([mci.getX(walker=w) for w in (0, 1, 4095)])))
+    for mode in (0, 1):
+        a = [r for r in res if r[0] == "1" and r[1] == mode][0]
+        b = [r for r in res if r[0] == "0" and r[1] == mode][0]
+        assert np.array_equal(a[2], b[2]) and a[3] == b[3] and np.array_equal(a[4], b[4])
