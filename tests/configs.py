@@ -65,6 +65,21 @@ RUNS = {
                      ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.5,), x0=_alt(16)),
     "ms_nosub8": dict(ndim=8, seed=5, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=4000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.3,),
                       x0=_alt(8)),
+    # --- edge cases
+    "vec_ortho_types": dict(ndim=6, seed=31, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 4, 1), (orc.OBS_X2SUM, 1, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=2,
+                            ntypes=3, type_ends=[2, 4, 6], steps=(1.5, 2.5, 3.5), lb=[-2., -3., -2., -3., -2., -3.], ub=[2., 3., 2., 3., 2., 3.],
+                            x0=[1.9, -2.9, 0.1, 0.2, -1.9, 2.9]),
+    "ms_ortho": dict(ndim=4, seed=8, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 2, 1)], nmc=4096, move_type=orc.MOVE_MULTISTEP, veclen=1, ms_nsteps=6,
+                     ms_sub_pdf_id=orc.PDF_GAUSS, steps=(0.8,), lb=-1.5, ub=1.5, x0=[1.4, -1.4, 0.3, 0.]),
+    "no_obs": dict(ndim=3, seed=77, pdf_id=orc.PDF_GAUSS3D, obs=[], nmc=5000, steps=(0.7,), x0=(1., 2., 3.)),
+    "calib_only": dict(ndim=3, seed=78, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=0, x0=(1., 2., 3.), do_find=True, do_decorr=True),
+    "nmc_one": dict(ndim=3, seed=79, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1), (orc.OBS_XYZSQUARED, 1, 1, False, orc.EST_NOOP)], nmc=1, steps=(1.0,),
+                    x0=(0.5, 0.5, 0.5)),
+    "nskip_gt_nmc": dict(ndim=3, seed=80, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1000), (orc.OBS_XYZSQUARED, 1, 7, False, orc.EST_NOOP)], nmc=500,
+                         steps=(1.0,), x0=(0.5, 0.5, 0.5)),
+    "full_two_samples": dict(ndim=1, seed=81, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 1, 1, False, orc.EST_UNCORRELATED)], nmc=2, steps=(2.0,)),
+    "vec_full_len": dict(ndim=3, seed=82, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=4096, move_type=orc.MOVE_VEC, veclen=3, steps=(0.9,)),
+    "block_skip_big": dict(ndim=2, seed=83, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 64, 3, True, orc.EST_UNCORRELATED)], nmc=64*3*40, steps=(1.1,)),
     # --- no sampling function (plain MC over a box), ex_basic
     "nopdf_box": dict(ndim=3, seed=42, pdf_id=orc.PDF_NONE, obs=[(orc.OBS_GAUSSXSQUARED, 1, 1)], nmc=16384, lb=-5., ub=5.),
     "exbasic_1": dict(ndim=1, seed=7, pdf_id=orc.PDF_NONE, obs=[(orc.OBS_PARABOLA, 1, 1)], nmc=100000, lb=-1., ub=3., x0=(-0.5,), steps=(0.25,), target_acc=0.7,

@@ -104,3 +104,30 @@ def test_fp32_prefilter_never_changes_a_decision(mcig, monkeypatch):
         a = [r for r in res if r[0] == "1" and r[1] == mode][0]
         b = [r for r in res if r[0] == "0" and r[1] == mode][0]
         assert np.array_equal(a[2], b[2]) and a[3] == b[3] and np.array_equal(a[4], b[4])
+
+
+def test_two_sampling_functions_multiply(mcig):
+    """SamplingFunctionContainer multiplies the acceptances of all pdfs (src/SamplingFunctionContainer.cpp:41-48):
+    exp(-r^2) * exp(-r^2) = exp(-2 r^2)  =>  <x^2> = 1/4 per coordinate. Also exercises the log-acceptance sum of the pre-filter."""
+    mci = mcig.MCI(3)
+    mci.setRngMode(0)
+    mci.setSeed(11)
+    mci.setNWalkers(1000)  # not a multiple of the block size
+    mci.addSamplingFunction(mcig.ThreeDimGaussianPDF())
+    mci.addSamplingFunction(mcig.Gauss(3))
+    mci.addObservable(mcig.XYZSquared(), 0, 1)
+    mci.setMRT2Step(0.8)
+    mci.integrate(2000, False, False)
+    avg, _ = mci.integrate(20000, False, False)
+    cw = mci.crossWalkerError()
+    assert np.all(np.abs(avg - 0.25) < 4.5*cw), (avg, cw)
+
+
+def test_walker_count_not_multiple_of_warp(mcig):
+    """Per-walker streams do not depend on how many walkers share the launch: walkers 0..32 of a 33-walker job equal those of a 1000-walker job."""
+    spec = dict(ndim=3, seed=5, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=3000, steps=(1.0,))
+    a = build_mci(mcig, spec, nwalkers=33, mode=0)
+    b = build_mci(mcig, spec, nwalkers=1000, mode=0)
+    a.integrate(3000, False, False)
+    b.integrate(3000, False, False)
+    assert np.array_equal(a.walkerResults()[0][0], b.walkerResults()[0][0, :33])

@@ -38,7 +38,8 @@ def test_replay_vs_oracle_and_golden(name, mcig, oracle, golden_runs):
     avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
     # bit-exact integer / control-flow quantities
     n = spec["nmc"]
-    assert round(mci.getAcceptanceRate()*n) == ref["n_acc"], "accept count differs"
+    if n > 0:
+        assert round(mci.getAcceptanceRate()*n) == ref["n_acc"], "accept count differs"
     assert mci.getAcceptanceRate() == ref["acc_rate"]
     assert list(mci.getX()) == ref["x_final"], "final position not bit-exact"
     nt = max(1, spec.get("ntypes", 1))
