@@ -496,6 +496,18 @@ __global__ void fcblocker_events_kernel(const double * __restrict__ data, i64 n,
     werr[col] = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
 }
 
+// ready-queue of the dynamically scheduled walk kernel: chunk 0 of every walker block is ready, the rest is produced at run time
+__global__ void dyn_init_kernel(int * __restrict__ queue, int * __restrict__ ctrl, int nblocks, int total)
+{
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < total) { queue[i] = (i < nblocks) ? i : -1; }
+    if (i == 0) {
+        ctrl[0] = 0;       // head ticket
+        ctrl[1] = nblocks; // tail ticket
+        ctrl[2] = 0;       // error flag
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- layout helpers
 // host-order [W][n] -> device-order [n][W] (replay draws, start positions)
 __global__ void transpose_kernel(const double * __restrict__ in, i64 W, i64 n, double * __restrict__ out)

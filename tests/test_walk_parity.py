@@ -169,3 +169,30 @@ def test_error_behaviour_on_device(mcig):
     mci = build_mci(mcig, dict(configs.RUNS["c1_simple_short"], obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_FCBLOCKER)]))
     with pytest.raises(McigError, match=">= 50"):
         mci.integrate(40, False, False)  # src/Estimators.cpp:196-198
+
+
+@pytest.mark.parametrize("name", ["c1_simple", "mixed", "block8_skip2_corr", "full_mj", "tp3g_small", "ms_default4", "all_types", "nopdf_box", "auto_default"])
+def test_dynamic_chunk_scheduling_bit_exact(name, mcig, oracle):
+    """The persistent, work-stealing variant of the register kernel cuts every chain into chunks that may run on different SMs;
+    chain state travels through L2. It must reproduce the oracle exactly like the static kernel (replay mode)."""
+    spec = configs.RUNS[name]
+    ref = oracle.run(configs.make(name))
+    mci = build_mci(mcig, spec, placement=0)
+    mci.setDynamicScheduling(1)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    assert mci.getAcceptanceRate() == ref["acc_rate"]
+    assert list(mci.getX()) == ref["x_final"]
+    assert _close(avg, ref["avg"], AVG_RTOL) and _close(err, ref["err"], ERR_RTOL, atol=1e-18)
+
+
+def test_dynamic_equals_static_in_philox_mode(mcig):
+    spec = dict(ndim=3, seed=4, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1), (orc.OBS_XYZSQUARED, 16, 2)], nmc=32768, steps=(1.0,))
+    out = []
+    for dyn in (0, 1):
+        mci = build_mci(mcig, spec, nwalkers=1000, mode=0)
+        mci.setDynamicScheduling(dyn)
+        avg, err = mci.integrate(32768, False, False)
+        wavg, werr = mci.walkerResults()
+        out.append((avg, err, wavg.copy(), werr.copy(), mci.getAcceptanceRate(), mci.getX(walker=999)))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))

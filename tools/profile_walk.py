@@ -8,6 +8,7 @@ import mcintegratorplusplus_b200 as m  # noqa: E402
 nmc = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 bs = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+dyn = int(sys.argv[4]) if len(sys.argv) > 4 else -1
 mci = m.MCI(3)
 mci.setRngMode(0)
 mci.setSeed(1337)
@@ -17,7 +18,9 @@ mci.addObservable(m.XSquared(), 0, 1)
 mci.setMRT2Step(1.0)
 if bs:
     mci.setBlockSize(bs)
+mci.setDynamicScheduling(dyn)
 for _ in range(3):
     avg, err = mci.integrate(nmc, False, False)
 t = mci.timings()
+print("dyn=%d " % dyn, end="")
 print("W=%d nmc=%d bs=%d walk %.3f ms -> %.4e steps/s, avg %.6f acc %.4f" % (W, nmc, bs, t["walk_ms"], W*nmc/(t["walk_ms"]*1e-3), avg[0], mci.getAcceptanceRate()))
