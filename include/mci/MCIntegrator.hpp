@@ -54,8 +54,9 @@ private:
 
     static int toSrrd(SRRDType t)
     {
-        if (t != SRRDType::Uniform) { throw std::domain_error("[MCI::setTrialMove] only SRRDType::Uniform has a device sampler so far"); }
-        return MCIG_SRRD_UNIFORM;
+        if (t == SRRDType::Uniform) { return MCIG_SRRD_UNIFORM; }
+        if (t == SRRDType::Gaussian) { return MCIG_SRRD_GAUSSIAN; }
+        throw std::domain_error("[MCI::setTrialMove] this SRRDType has no device sampler yet (available: Uniform, Gaussian)");
     }
 
     void pushConfiguration()

@@ -24,8 +24,9 @@ class MoveType(IntEnum):  # include/mci/Factories.hpp:108-114
     MultiStep = 2
 
 
-class SRRDType(IntEnum):  # include/mci/Factories.hpp:119-133 (device samplers: uniform only so far)
+class SRRDType(IntEnum):  # include/mci/Factories.hpp:119-133 (the distributions with a device sampler)
     Uniform = 0
+    Gaussian = 1
 
 
 class EstimatorType(IntEnum):  # include/mci/Factories.hpp:52-59
@@ -211,13 +212,15 @@ class MCI:
         if typeEnds is not None:
             te_arr = np.ascontiguousarray(typeEnds, dtype=np.int32)
             te = te_arr.ctypes.data_as(C.POINTER(C.c_int))
+        srrd = 0
         if isinstance(move, MoveType):
             mt = int(move)
             vl = veclen if veclen > 0 else 1
         else:  # SRRDType: veclen 0 = all-move
             mt = int(MoveType.Vec) if veclen > 0 else int(MoveType.All)
             vl = max(1, veclen)
-        _capi.check(self._lib.mcig_set_move(self._ctx, mt, 0, vl, ntypes, te))
+            srrd = int(move)
+        _capi.check(self._lib.mcig_set_move(self._ctx, mt, srrd, vl, ntypes, te))
         if mt == int(MoveType.MultiStep):
             _capi.check(self._lib.mcig_multistep_config(self._ctx, int(nsteps)))
             for pdf in sub_pdfs:

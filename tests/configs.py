@@ -65,6 +65,14 @@ RUNS = {
                      ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.5,), x0=_alt(16)),
     "ms_nosub8": dict(ndim=8, seed=5, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=4000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.3,),
                       x0=_alt(8)),
+    # --- Gaussian proposals (SRRDType::Gaussian: std::normal_distribution, polar method with a cached value)
+    "gauss_all": dict(ndim=3, seed=99, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 16, 1)], nmc=16384, srrd=orc.SRRD_GAUSSIAN, steps=(0.6,)),
+    "gauss_all_auto": dict(ndim=3, seed=98, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=8192, srrd=orc.SRRD_GAUSSIAN, x0=(2., -2., 1.),
+                           do_find=True, do_decorr=True),
+    "gauss_vec5": dict(ndim=5, seed=97, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 1), (orc.OBS_XND, 0, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=1,
+                       srrd=orc.SRRD_GAUSSIAN, steps=(1.2,)),
+    "gauss_vec6_v3": dict(ndim=6, seed=96, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_X2SUM, 8, 1)], nmc=16384, move_type=orc.MOVE_VEC, veclen=3,
+                          srrd=orc.SRRD_GAUSSIAN, steps=(0.9,), lb=-4., ub=4.),
     # --- edge cases
     "vec_ortho_types": dict(ndim=6, seed=31, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 4, 1), (orc.OBS_X2SUM, 1, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=2,
                             ntypes=3, type_ends=[2, 4, 6], steps=(1.5, 2.5, 3.5), lb=[-2., -3., -2., -3., -2., -3.], ub=[2., 3., 2., 3., 2., 3.],

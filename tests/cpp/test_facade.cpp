@@ -67,7 +67,9 @@ static void test_api()
     assert(throws<std::invalid_argument>([&] { mci.setTrialMove(SRRDType::Uniform, 2); }));
     assert(throws<std::invalid_argument>([&] { mci.setIRange(1., -1.); }));
     assert(throws<std::invalid_argument>([&] { mci.setDomain(OrthoPeriodicDomain(2, -1., 1.)); }));
-    assert(throws<std::domain_error>([&] { mci.setTrialMove(SRRDType::Gaussian); }));
+    assert(throws<std::domain_error>([&] { mci.setTrialMove(SRRDType::Cauchy); }));
+    mci.setTrialMove(SRRDType::Gaussian);
+    assert(mci.getTrialMove().getSRRDType() == SRRDType::Gaussian);
     assert(throws<std::invalid_argument>([] { selectEstimatorType(true, false); }));
     MultiStepMove msm(3);
     assert(msm.getNSteps() == 3 && msm.getChangeRate() == 1.);

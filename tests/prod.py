@@ -23,10 +23,11 @@ def build_mci(m, spec, nwalkers=1, mode=None, seeds=None, placement=None):
     mt = kw.get("move_type", orc.MOVE_ALL)
     ntypes = kw.get("ntypes", 1)
     te = kw.get("type_ends")
+    srrd = m.SRRDType(kw.get("srrd", 0))
     if mt == orc.MOVE_ALL:
-        mci.setTrialMove(m.SRRDType.Uniform, 0, ntypes, te)
+        mci.setTrialMove(srrd, 0, ntypes, te)
     elif mt == orc.MOVE_VEC:
-        mci.setTrialMove(m.SRRDType.Uniform, max(1, kw.get("veclen", 1)), ntypes, te)
+        mci.setTrialMove(srrd, max(1, kw.get("veclen", 1)), ntypes, te)
     else:
         sub = []
         if kw.get("ms_sub_pdf_id", 0):

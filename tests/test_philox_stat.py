@@ -48,7 +48,7 @@ def test_philox_results_independent_of_sharding_and_launch_chunking(mcig):
     assert np.array_equal(two.getX(walker=7), full.getX(walker=7))
 
 
-@pytest.mark.parametrize("name", ["mixed", "vec_exp4", "ms_sub_ut5", "ndim_vec16", "exbasic_2", "nopdf_box", "ut4_fixed"])
+@pytest.mark.parametrize("name", ["mixed", "vec_exp4", "ms_sub_ut5", "ndim_vec16", "exbasic_2", "nopdf_box", "ut4_fixed", "gauss_all_auto", "gauss_vec5"])
 def test_families_within_three_sigma_of_reference(name, mcig, oracle):
     spec = dict(configs.RUNS[name])
     ref = oracle.run(configs.make(name))
@@ -131,3 +131,22 @@ def test_walker_count_not_multiple_of_warp(mcig):
     a.integrate(3000, False, False)
     b.integrate(3000, False, False)
     assert np.array_equal(a.walkerResults()[0][0], b.walkerResults()[0][0, :33])
+
+
+def test_box_muller_proposals_are_standard_normal(mcig):
+    """Philox-mode Gaussian proposals: with no sampling function every proposal... is not available (no-pdf mode samples the box),
+    so check through the chain instead: a Gaussian all-move of step s on a FLAT direction. Use ExpND pdf in 1-D with a huge box:
+    simpler and sharper — the calibrated acceptance of a 1-D standard normal target under N(0, s^2) proposals is known:
+    acc(s) = (2/pi) * atan(2/s). For s = 2: 0.5."""
+    mci = mcig.MCI(1)
+    mci.setRngMode(0)
+    mci.setSeed(77)
+    mci.setNWalkers(4096)
+    mci.setTrialMove(mcig.SRRDType.Gaussian)
+    mci.addSamplingFunction(mcig.Gauss(1))  # exp(-x^2): sigma^2 = 1/2  => in units of sigma the step below is 2*sqrt(2)*0.5
+    mci.addObservable(mcig.X2(1), 0, 1)
+    mci.setMRT2Step(np.sqrt(2.0))            # proposal sigma = 2 target sigmas
+    mci.integrate(500, False, False)
+    avg, _ = mci.integrate(4000, False, False)
+    assert abs(avg[0] - 0.5) < 5*mci.crossWalkerError()[0]
+    assert abs(mci.getAcceptanceRate() - (2/np.pi)*np.arctan(2/2.0)) < 2e-3
