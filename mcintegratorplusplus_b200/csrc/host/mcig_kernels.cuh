@@ -130,6 +130,16 @@ __global__ void uncorr_partial_kernel(const double * __restrict__ data, i64 n, i
     part[((i64)seg*2 + 1)*ncol + col] = q;
 }
 
+// column sums from the per-segment partials (sum part only), segments added in order
+__global__ void sum_partials_kernel(const double * __restrict__ part, i64 ncol, int nseg, double * __restrict__ sums)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    double s = 0.;
+    for (int seg = 0; seg < nseg; ++seg) { s = __dadd_rn(s, part[((i64)seg*2 + 0)*ncol + col]); }
+    sums[col] = s;
+}
+
 // nobs_is_one selects the 1-D formula sqrt(var/(n-1.)) vs the N-D one sqrt(var*(1./(n-1.))) (Estimators.cpp:49-50 vs :147-150)
 __global__ void uncorr_finish_kernel(const double * __restrict__ part, i64 n, i64 ncol, int nseg, int nobs_is_one, double * __restrict__ wavg,
                                      double * __restrict__ werr)
