@@ -54,9 +54,7 @@ private:
 
     static int toSrrd(SRRDType t)
     {
-        if (t == SRRDType::Uniform) { return MCIG_SRRD_UNIFORM; }
-        if (t == SRRDType::Gaussian) { return MCIG_SRRD_GAUSSIAN; }
-        throw std::domain_error("[MCI::setTrialMove] this SRRDType has no device sampler yet (available: Uniform, Gaussian)");
+        return static_cast<int>(t); // same enumerator order as MCIG_SRRD_* (include/mci/Factories.hpp:119-133)
     }
 
     void pushConfiguration()

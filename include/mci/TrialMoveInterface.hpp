@@ -1,8 +1,8 @@
 // Trial moves — mirror of include/mci/TrialMoveInterface.hpp:16-70, TypedMoveInterface.hpp:20-63, SRRDAllMove.hpp,
 // SRRDVecMove.hpp, MultiStepMove.hpp. The proposal itself runs in the walk kernel (device/mcig_device.cuh, MOVE 0/1/2);
 // these host objects carry the move's configuration (kind, vector length, typed step sizes, MultiStep sub-move and
-// sub-sampling functions) and the step-size accessors findMRT2Step needs. Only the uniform distribution has a device
-// sampler so far: the other SRRDType enumerators are accepted by the factories and rejected by MCI.
+// sub-sampling functions) and the step-size accessors findMRT2Step needs. All ten SRRDType distributions have device samplers
+// (device/mcig_device.cuh: Proposal); MultiStepMove sub-moves are uniform single-vector moves.
 #ifndef MCIG_MCI_TRIALMOVEINTERFACE_HPP
 #define MCIG_MCI_TRIALMOVEINTERFACE_HPP
 

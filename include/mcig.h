@@ -33,7 +33,11 @@ enum {
 
 /* include/mci/Factories.hpp:108-145 */
 enum { MCIG_MOVE_ALL = 0, MCIG_MOVE_VEC = 1, MCIG_MOVE_MULTISTEP = 2 };
-enum { MCIG_SRRD_UNIFORM = 0, MCIG_SRRD_GAUSSIAN = 1 }; /* include/mci/Factories.hpp:119-133: the distributions with a device sampler */
+/* SRRDType, include/mci/Factories.hpp:119-133 (default parameters of createSymRRD<>, include/mci/TrialMoveInterface.hpp:113-187) */
+enum {
+    MCIG_SRRD_UNIFORM = 0, MCIG_SRRD_GAUSSIAN = 1, MCIG_SRRD_STUDENT = 2, MCIG_SRRD_CAUCHY = 3, MCIG_SRRD_EXPONENTIAL = 4,
+    MCIG_SRRD_GAMMA = 5, MCIG_SRRD_WEIBULL = 6, MCIG_SRRD_LOGNORMAL = 7, MCIG_SRRD_CHISQ = 8, MCIG_SRRD_FISHER = 9
+};
 /* include/mci/Factories.hpp:52-59 */
 enum { MCIG_EST_NOOP = 0, MCIG_EST_UNCORRELATED = 1, MCIG_EST_CORRELATED = 2, MCIG_EST_FCBLOCKER = 3, MCIG_EST_MJBLOCKER = 4 };
 /* random number source of the walk kernel */

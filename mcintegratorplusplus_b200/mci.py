@@ -24,9 +24,17 @@ class MoveType(IntEnum):  # include/mci/Factories.hpp:108-114
     MultiStep = 2
 
 
-class SRRDType(IntEnum):  # include/mci/Factories.hpp:119-133 (the distributions with a device sampler)
+class SRRDType(IntEnum):  # include/mci/Factories.hpp:119-133
     Uniform = 0
     Gaussian = 1
+    Student = 2
+    Cauchy = 3
+    Exponential = 4
+    Gamma = 5
+    Weibull = 6
+    Lognormal = 7
+    Chisq = 8
+    Fisher = 9
 
 
 class EstimatorType(IntEnum):  # include/mci/Factories.hpp:52-59

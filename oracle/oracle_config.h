@@ -49,7 +49,8 @@ enum {
 
 /* trial moves: include/mci/Factories.hpp:108-145 */
 enum { ORC_MOVE_ALL = 0, ORC_MOVE_VEC = 1, ORC_MOVE_MULTISTEP = 2 };
-/* SRRD distribution of the (sub-)move: only those with a device sampler are listed */
+/* SRRD distribution of the move, include/mci/Factories.hpp:119-133. The C restatement covers 0 and 1; 2..9 (Student, Cauchy,
+   Exponential, Gamma, Weibull, Lognormal, Chisq, Fisher) are available through the reference harness only (goldens). */
 enum { ORC_SRRD_UNIFORM = 0, ORC_SRRD_GAUSSIAN = 1 };
 /* estimator types: include/mci/Factories.hpp:52-59 */
 enum { ORC_EST_NOOP = 0, ORC_EST_UNCORRELATED = 1, ORC_EST_CORRELATED = 2, ORC_EST_FCBLOCKER = 3, ORC_EST_MJBLOCKER = 4 };

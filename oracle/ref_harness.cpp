@@ -94,8 +94,10 @@ static void configure(MCI &mci, const orc_config_t &c)
     // move
     const int ntypes = std::max(1, c.ntypes);
     std::vector<int> tends(c.type_ends, c.type_ends + ORC_MAXTYPES);
-    if (c.srrd != ORC_SRRD_UNIFORM && c.srrd != ORC_SRRD_GAUSSIAN) { throw std::invalid_argument("ref_harness: unsupported srrd"); }
-    const SRRDType srrd = (c.srrd == ORC_SRRD_GAUSSIAN) ? SRRDType::Gaussian : SRRDType::Uniform;
+    if (c.srrd < 0 || c.srrd > 9) { throw std::invalid_argument("ref_harness: unsupported srrd"); }
+    static const SRRDType kinds[10] = {SRRDType::Uniform, SRRDType::Gaussian, SRRDType::Student, SRRDType::Cauchy, SRRDType::Exponential,
+                                       SRRDType::Gamma, SRRDType::Weibull, SRRDType::Lognormal, SRRDType::Chisq, SRRDType::Fisher};
+    const SRRDType srrd = kinds[c.srrd];
     if (c.move_type == ORC_MOVE_ALL) {
         mci.setTrialMove(srrd, 0, ntypes, ntypes > 1 ? tends.data() : nullptr);
     }

@@ -73,6 +73,16 @@ RUNS = {
                        srrd=orc.SRRD_GAUSSIAN, steps=(1.2,)),
     "gauss_vec6_v3": dict(ndim=6, seed=96, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_X2SUM, 8, 1)], nmc=16384, move_type=orc.MOVE_VEC, veclen=3,
                           srrd=orc.SRRD_GAUSSIAN, steps=(0.9,), lb=-4., ub=4.),
+    # --- the other eight SRRD proposal distributions (createSymRRD defaults). Reference values come from the harness only (goldens):
+    #     the C oracle restates uniform and normal; the CUDA path replays the libstdc++ outputs of all of them.
+    "srrd_student_all": dict(ndim=3, seed=201, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=8192, srrd=2, steps=(0.4,)),
+    "srrd_cauchy_vec": dict(ndim=4, seed=202, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 8, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=2, srrd=3, steps=(0.5,)),
+    "srrd_exponential_all": dict(ndim=3, seed=203, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XYZSQUARED, 0, 1)], nmc=8192, srrd=4, steps=(0.6,), do_find=True, do_decorr=True),
+    "srrd_gamma_vec": dict(ndim=3, seed=204, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 16, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=1, srrd=5, steps=(1.0,)),
+    "srrd_weibull_all": dict(ndim=2, seed=205, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1)], nmc=8192, srrd=6, steps=(0.7,)),
+    "srrd_lognormal_all": dict(ndim=3, seed=206, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=8192, srrd=7, steps=(0.3,)),
+    "srrd_chisq_vec": dict(ndim=6, seed=207, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 2)], nmc=8192, move_type=orc.MOVE_VEC, veclen=3, srrd=8, steps=(0.4,)),
+    "srrd_fisher_all": dict(ndim=1, seed=208, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 32, 1)], nmc=8192, srrd=9, steps=(0.5,), lb=-6., ub=6.),
     # --- edge cases
     "vec_ortho_types": dict(ndim=6, seed=31, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 4, 1), (orc.OBS_X2SUM, 1, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=2,
                             ntypes=3, type_ends=[2, 4, 6], steps=(1.5, 2.5, 3.5), lb=[-2., -3., -2., -3., -2., -3.], ub=[2., 3., 2., 3., 2., 3.],
@@ -95,6 +105,11 @@ RUNS = {
     "exbasic_2": dict(ndim=1, seed=7, pdf_id=orc.PDF_NORMLINE, obs=[(orc.OBS_NORMPARABOLA, 1, 1)], nmc=100000, lb=-1., ub=3., x0=(-0.5,), steps=(0.25,),
                       target_acc=0.7, do_find=True, do_decorr=True),
 }
+
+
+def in_oracle(name):
+    """The plain-C oracle restates the uniform and normal proposal distributions; the rest is pinned by the goldens only."""
+    return RUNS[name].get("srrd", 0) < 2
 
 
 def make(name):

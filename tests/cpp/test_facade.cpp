@@ -67,7 +67,8 @@ static void test_api()
     assert(throws<std::invalid_argument>([&] { mci.setTrialMove(SRRDType::Uniform, 2); }));
     assert(throws<std::invalid_argument>([&] { mci.setIRange(1., -1.); }));
     assert(throws<std::invalid_argument>([&] { mci.setDomain(OrthoPeriodicDomain(2, -1., 1.)); }));
-    assert(throws<std::domain_error>([&] { mci.setTrialMove(SRRDType::Cauchy); }));
+    mci.setTrialMove(SRRDType::Cauchy, 1);
+    assert(mci.getTrialMove().getMoveType() == MoveType::Vec && mci.getTrialMove().getSRRDType() == SRRDType::Cauchy);
     mci.setTrialMove(SRRDType::Gaussian);
     assert(mci.getTrialMove().getSRRDType() == SRRDType::Gaussian);
     assert(throws<std::invalid_argument>([] { selectEstimatorType(true, false); }));

@@ -35,7 +35,8 @@ def test_builtin_plugins_registered(mcig):
 
 
 @pytest.mark.parametrize("name", ["c1_simple", "mixed", "vec_exp4", "ndim_vec16", "ms_sub_ut5", "ms_sub16", "nopdf_box", "ut2_irange", "vec3_types",
-                                  "ndim_all64", "ndim_vec64_v4", "gauss_all", "gauss_vec5", "gauss_vec6_v3"])
+                                  "ndim_all64", "ndim_vec64_v4", "gauss_all", "gauss_vec5", "gauss_vec6_v3", "srrd_student_all", "srrd_cauchy_vec", "srrd_exponential_all", "srrd_lognormal_all",
+                                  "srrd_chisq_vec", "srrd_fisher_all"])
 @pytest.mark.parametrize("mode", [0, 2])
 def test_jit_compiles_without_gpu(name, mode, mcig, tmp_path, monkeypatch):
     monkeypatch.setenv("MCIG_CACHE_DIR", str(tmp_path))

@@ -10,8 +10,9 @@ PKG = os.path.join(ROOT, "mcintegratorplusplus_b200")
 
 
 def _compile(src, out):
-    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-L" + PKG, "-lmcig",
-           "-Wl,-rpath," + PKG, "-o", out]
+    cc = ["gcc", "-std=c99"] if src.endswith(".c") else ["g++", "-std=c++14"]
+    cmd = cc + ["-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-L" + PKG, "-lmcig", "-lm",
+                "-Wl,-rpath," + PKG, "-o", out]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return out
 
@@ -38,3 +39,16 @@ def test_ex_basic_on_gpu(mcig, tmp_path):
     out = subprocess.run([exe, "512"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.strip().endswith("OK")
+
+
+def test_plain_c_binding_api(mcig, tmp_path):
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_capi.c"), str(tmp_path / "test_capi"))
+    out = subprocess.run([exe, "api"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "capi api ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_binding_on_gpu(mcig, tmp_path):
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_capi.c"), str(tmp_path / "test_capi"))
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "capi gpu ok" in out.stdout, out.stdout + out.stderr

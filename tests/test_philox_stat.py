@@ -150,3 +150,23 @@ def test_box_muller_proposals_are_standard_normal(mcig):
     avg, _ = mci.integrate(4000, False, False)
     assert abs(avg[0] - 0.5) < 5*mci.crossWalkerError()[0]
     assert abs(mci.getAcceptanceRate() - (2/np.pi)*np.arctan(2/2.0)) < 2e-3
+
+
+@pytest.mark.parametrize("srrd", list(range(10)))
+def test_every_srrd_distribution_samples_the_target(srrd, mcig):
+    """Any symmetric proposal leaves the target invariant: <x_i^2> = 1/2 for exp(-r^2) with all ten SRRDType proposals
+    (closed-form device samplers in Philox mode), all-move and single-vector move."""
+    for veclen in (0, 1):
+        mci = mcig.MCI(3)
+        mci.setRngMode(0)
+        mci.setSeed(300 + srrd)
+        mci.setNWalkers(2048)
+        mci.setTrialMove(mcig.SRRDType(srrd), veclen)
+        mci.addSamplingFunction(mcig.Gauss(3))
+        mci.addObservable(mcig.XYZSquared(), 0, 1)
+        mci.setMRT2Step(0.5)
+        mci.integrate(3000, False, False)
+        avg, _ = mci.integrate(6000, False, False)
+        cw = mci.crossWalkerError()
+        assert 0.05 < mci.getAcceptanceRate() < 0.98
+        assert np.all(np.abs(avg - 0.5) < 5*cw), (srrd, veclen, avg, cw)

@@ -30,10 +30,13 @@ def _close(a, b, rtol, atol=1e-15):
 @pytest.mark.parametrize("name", sorted(configs.RUNS))
 def test_replay_vs_oracle_and_golden(name, mcig, oracle, golden_runs):
     spec = configs.RUNS[name]
-    cfg = configs.make(name)
-    ref = oracle.run(cfg)
     g = golden_runs[name]
-    assert ref["avg"] == fromhex(g["avg"])  # oracle itself is pinned to the reference
+    if configs.in_oracle(name):
+        ref = oracle.run(configs.make(name))
+        assert ref["avg"] == fromhex(g["avg"])  # oracle itself is pinned to the reference
+    else:  # distributions the C oracle does not restate: the reference's own outputs (goldens) are the checker
+        ref = {"avg": fromhex(g["avg"]), "err": fromhex(g["err"]), "acc_rate": float.fromhex(g["acc_rate"]), "x_final": fromhex(g["x_final"]),
+               "steps_final": fromhex(g["steps_final"]), "n_acc": g["n_acc"]}
     mci = build_mci(mcig, spec)
     avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
     # bit-exact integer / control-flow quantities
