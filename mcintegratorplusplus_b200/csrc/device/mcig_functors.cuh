@@ -16,6 +16,8 @@
 //       // optional (registration flag MCIG_PLUGIN_LOG_ACCEPTANCE): log of acceptanceFunction. When every sampling function
 //       // of an integrator provides it, production modes test u <= exp(sum of logs) with an FP32 pre-filter (accept_log).
 //       template <class PO, class PN> __device__ double logAcceptance(const PO & po, const PN & pn) const;
+//       // with HAS_UPDATE as well: the selective counterpart (updates protonew like updatedAcceptance, returns the log)
+//       template <class W, class PO, class PN> __device__ double updatedLogAcceptance(const W & wlk, const PO & po, PN & pn) const;
 //   };
 //   struct MyObs {                                  // mirrors mci::ObservableFunctionInterface
 //       static constexpr int NPAR = 0;
@@ -105,6 +107,19 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
         }
         return exp(-expf);
     }
+    template <class W, class PO, class PN>
+    MCIG_DEV double updatedLogAcceptance(const W & wlk, const PO & po, PN & pn) const
+    {
+        double expf = 0.;
+        for (int i = 0; i < wlk.nchanged; ++i) {
+            const int k = wlk.changedIdx[i];
+            const double xk = wlk.xnew[k];
+            const double v = xk*xk;
+            pn[k] = v;
+            expf += v - po[k];
+        }
+        return -expf;
+    }
 };
 
 struct Exp1DPDF { // TestMCIFunctions.hpp:189-215
@@ -173,6 +188,18 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
             expf += v - po[k];
         }
         return exp(-expf);
+    }
+    template <class W, class PO, class PN>
+    MCIG_DEV double updatedLogAcceptance(const W & wlk, const PO & po, PN & pn) const
+    {
+        double expf = 0.;
+        for (int i = 0; i < wlk.nchanged; ++i) {
+            const int k = wlk.changedIdx[i];
+            const double v = fabs(wlk.xnew[k]);
+            pn[k] = v;
+            expf += v - po[k];
+        }
+        return -expf;
     }
 };
 

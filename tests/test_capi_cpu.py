@@ -97,3 +97,17 @@ def test_no_cpu_fallback(mcig):
         mcig.estimate(mcig.EstimatorType.Uncorrelated, np.arange(64.))
     with pytest.raises(_capi.McigError, match="no CUDA device"):
         mcig.measure_peaks()
+
+
+def test_oversized_walker_fails_with_a_clear_message(mcig):
+    """One chain per thread keeps the walker on chip; a walker that cannot fit must be refused loudly, not crash at launch."""
+    from mcintegratorplusplus_b200._capi import McigError
+    mci = mcig.MCI(512)
+    mci.addSamplingFunction(mcig.Gauss(512))
+    mci.addObservable(mcig.X2Sum(512), 0, 1)
+    with pytest.raises(McigError, match="shared memory"):
+        mci.prebuild()
+    ok = mcig.MCI(128)  # 131 KiB per warp of walkers: fits
+    ok.addSamplingFunction(mcig.Gauss(128))
+    ok.addObservable(mcig.X2Sum(128), 0, 1)
+    ok.prebuild()

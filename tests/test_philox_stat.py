@@ -87,23 +87,34 @@ def test_symmetric_expectations_exact(name, exact, mcig):
     assert np.all(np.abs(avg - exact) < 4.5*cw + 1e-12), (avg, cw)
 
 
-def test_fp32_prefilter_never_changes_a_decision(mcig, monkeypatch):
+PREFILTER_SPECS = {
+    "all3_reg": dict(ndim=3, seed=2024, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=20000, steps=(1.0,), x0=(0.3, -0.1, 0.2)),
+    "vec8_smem": dict(ndim=8, seed=2025, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_X2SUM, 0, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,)),
+    "vec6_v2_gauss_smem": dict(ndim=6, seed=2026, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 0, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=2, steps=(0.9,)),
+    "all32_smem": dict(ndim=32, seed=2027, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 0, 1)], nmc=4000, steps=(0.2,)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(PREFILTER_SPECS))
+def test_fp32_prefilter_never_changes_a_decision(case, mcig, monkeypatch):
     """The FP32 pre-filter of the accept test (device/mcig_device.cuh:accept_log) must give exactly the decisions of the plain
-    FP64 test u <= exp(d): same seed, same streams => bit-identical per-walker averages, positions and acceptance counts."""
-    spec = dict(ndim=3, seed=2024, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=20000, steps=(1.0,), x0=(0.3, -0.1, 0.2))
+    FP64 test u <= exp(d): same seed, same streams => bit-identical per-walker averages, positions and acceptance counts
+    (register and shared-memory kernels, full and selective acceptance paths, 32- and 53-bit uniforms)."""
+    spec = PREFILTER_SPECS[case]
     res = []
     for flag in ("1", "0"):
         monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_ACCEPT_PREFILTER=" + flag)
         for mode in (0, 1):
-            mci = build_mci(mcig, spec, nwalkers=4096, mode=mode)
+            mci = build_mci(mcig, spec, nwalkers=2048, mode=mode)
             assert ("MCIG_ACCEPT_PREFILTER " + flag) in mci.kernelSource()
-            mci.integrate(20000, False, False)
+            mci.integrate(spec["nmc"], False, False)
             wavg, _ = mci.walkerResults()
-            res.append((flag, mode, wavg.copy(), mci.getAcceptanceRate(), np.array([mci.getX(walker=w) for w in (0, 1, 4095)])))
+            res.append((flag, mode, wavg.copy(), mci.getAcceptanceRate(), np.array([mci.getX(walker=w) for w in (0, 1, 2047)])))
     for mode in (0, 1):
         a = [r for r in res if r[0] == "1" and r[1] == mode][0]
         b = [r for r in res if r[0] == "0" and r[1] == mode][0]
         assert np.array_equal(a[2], b[2]) and a[3] == b[3] and np.array_equal(a[4], b[4])
+        assert 0.2 < a[3] < 0.8
 
 
 def test_two_sampling_functions_multiply(mcig):
