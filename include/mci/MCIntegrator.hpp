@@ -326,6 +326,7 @@ public:
     void setRngMode(RngMode mode) { detail::check(mcig_set_rng_mode(_ctx, static_cast<int>(mode))); }
     void setWalkerSeeds(const uint64_t seeds[], int64_t n) { detail::check(mcig_set_walker_seeds(_ctx, seeds, n)); }
     void setDevice(int device) { detail::check(mcig_set_device(_ctx, device)); }
+    void setPhiloxRounds(int rounds) { detail::check(mcig_set_philox_rounds(_ctx, rounds)); }
     void setAllreduce(mcig_allreduce_fn fn, void * user) { detail::check(mcig_set_allreduce(_ctx, fn, user)); }
     void getCrossWalkerError(double err[]) const { detail::check(mcig_get_cross_walker_error(_ctx, err)); }
     void getWalkerResults(double avg[], double err[]) const { detail::check(mcig_get_walker_results(_ctx, avg, err)); }

