@@ -6,8 +6,8 @@
 //   * setNWalkers(W): one MCI runs W independent chains ("virtual MPI ranks", src/MPIMCI.cpp:83); W defaults to 1.
 //     integrate() returns the MPIMCI combination over walkers (avg of per-walker averages, sqrt(sum err^2)/W).
 //   * setRngMode(): Philox4x32-10 in registers (default) or replay of per-walker std::mt19937_64 streams (bit-exact parity).
-//   * setCallback / store*OnFile are not available: a per-step host callback cannot exist in a device-resident loop
-//     (out of scope for the hot path).
+//   * setCallback is not available: a per-step host callback cannot exist in a device-resident loop.
+//     storeObservablesOnFile / storeWalkerPositionsOnFile work (walker 0, written after the run).
 #ifndef MCIG_MCI_MCINTEGRATOR_HPP
 #define MCIG_MCI_MCINTEGRATOR_HPP
 
@@ -278,13 +278,14 @@ public:
         _dirtyPdf = true;
     }
 
-    // --- not available on the device path (see header comment)
+    // --- per-step host callbacks are not available on the device path (see header comment)
     void setCallback(const std::function<void(const MCI &)> &) { throw std::logic_error("[MCI::setCallback] per-step host callbacks are not available in the device-resident walk"); }
     void clearCallback() {}
-    void storeObservablesOnFile(const std::string &, int) { throw std::logic_error("[MCI::storeObservablesOnFile] not available in the device-resident walk"); }
-    void storeWalkerPositionsOnFile(const std::string &, int) { throw std::logic_error("[MCI::storeWalkerPositionsOnFile] not available in the device-resident walk"); }
-    void clearObservableFile() {}
-    void clearWalkerFile() {}
+    // file dumps of walker 0 every freq-th step (src/MCIntegrator.cpp:495-542), written after the run from device-side accumulators
+    void storeObservablesOnFile(const std::string & filepath, int freq) { detail::check(mcig_store_on_file(_ctx, 0, filepath.c_str(), freq)); }
+    void clearObservableFile() { detail::check(mcig_store_on_file(_ctx, 0, "", 0)); }
+    void storeWalkerPositionsOnFile(const std::string & filepath, int freq) { detail::check(mcig_store_on_file(_ctx, 1, filepath.c_str(), freq)); }
+    void clearWalkerFile() { detail::check(mcig_store_on_file(_ctx, 1, "", 0)); }
 
     // --- Getters
     int getNDim() const { return _ndim; }

@@ -154,6 +154,10 @@ int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double 
 /* ---- engine knobs without reference analogue */
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
 int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory */
+/* MCI::storeObservablesOnFile (what = 0) / storeWalkerPositionsOnFile (what = 1), src/MCIntegrator.cpp:495-542: text dump of
+ * walker 0 every freq-th step of the main sampling run ("ridx v0 v1 ..."), written after the run from device-side shadow
+ * accumulators. path NULL or "" switches the dump off (clearObservableFile / clearWalkerFile). */
+int mcig_store_on_file(mcig_ctx * ctx, int what, const char * path, int freq);
 /* rounds of the Philox4x32 generator: 10 (default, the standard Philox4x32-10) down to 7 (the smallest variant that passes
  * BigCrush according to Salmon et al., SC'11; +13..20 % throughput on RNG-bound integrands) */
 int mcig_set_philox_rounds(mcig_ctx * ctx, int rounds);

@@ -318,6 +318,10 @@ class MCI:
 
     def setBlockSize(self, n): _capi.check(self._lib.mcig_set_block_size(self._ctx, int(n)))
     def setStatePlacement(self, p): _capi.check(self._lib.mcig_set_state_placement(self._ctx, int(p)))
+    def storeObservablesOnFile(self, path, freq): _capi.check(self._lib.mcig_store_on_file(self._ctx, 0, path.encode(), int(freq)))
+    def storeWalkerPositionsOnFile(self, path, freq): _capi.check(self._lib.mcig_store_on_file(self._ctx, 1, path.encode(), int(freq)))
+    def clearObservableFile(self): _capi.check(self._lib.mcig_store_on_file(self._ctx, 0, b"", 0))
+    def clearWalkerFile(self): _capi.check(self._lib.mcig_store_on_file(self._ctx, 1, b"", 0))
     def setPhiloxRounds(self, rounds): _capi.check(self._lib.mcig_set_philox_rounds(self._ctx, int(rounds)))
     def setDynamicScheduling(self, mode): _capi.check(self._lib.mcig_set_dynamic_scheduling(self._ctx, int(mode)))
     def prebuild(self): _capi.check(self._lib.mcig_prebuild(self._ctx))

@@ -46,6 +46,17 @@ def main():
     with open(os.path.join(OUT, "ref_runs.json"), "w") as f:
         json.dump(runs, f, indent=1, sort_keys=True)
 
+    # periodic text dumps (storeObservablesOnFile / storeWalkerPositionsOnFile) of one small run
+    import ctypes as C
+    f = ref.lib.mciref_run_with_files
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(orc.Config), C.POINTER(orc.Result), C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    cfg = configs.make("dump_files")
+    res = orc.Result()
+    assert f(C.byref(cfg), C.byref(res), os.path.join(OUT, "dump_observables.txt").encode(), configs.DUMP_OBS_FREQ,
+             os.path.join(OUT, "dump_walker.txt").encode(), configs.DUMP_WLK_FREQ) == 0
+    print("dump_files", list(res.avg[:res.nobsdim]))
+
     est = {}
     for wname, (pdf, nmc, ndim, step, cp, seed) in configs.WALKS.items():
         datax, datacc, nchanged, cidx, rate = ref.testwalk(pdf, nmc, ndim, step, cp, seed)

@@ -219,6 +219,32 @@ int mciref_run(const orc_config_t * cfg, orc_result_t * res, orc_trace_t * trace
     }
 }
 
+// integrate() with the reference's periodic text dumps switched on (src/MCIntegrator.cpp:495-542): golden files for the
+// device-side replacement of storeObservablesOnFile / storeWalkerPositionsOnFile.
+int mciref_run_with_files(const orc_config_t * cfg, orc_result_t * res, const char * obs_path, int obs_freq, const char * wlk_path, int wlk_freq)
+{
+    try {
+        const orc_config_t &c = *cfg;
+        MCI mci(c.ndim);
+        configure(mci, c);
+        if (obs_path != nullptr && obs_freq > 0) { mci.storeObservablesOnFile(obs_path, obs_freq); }
+        if (wlk_path != nullptr && wlk_freq > 0) { mci.storeWalkerPositionsOnFile(wlk_path, wlk_freq); }
+        const int nobsdim = mci.getNObsDim();
+        std::vector<double> avg(std::max(1, nobsdim), 0.), err(std::max(1, nobsdim), 0.);
+        mci.integrate(c.nmc, avg.data(), err.data(), c.do_find != 0, c.do_decorr != 0);
+        std::memset(res, 0, sizeof(*res));
+        res->nobsdim = nobsdim;
+        std::copy(avg.begin(), avg.begin() + nobsdim, res->avg);
+        std::copy(err.begin(), err.begin() + nobsdim, res->err);
+        res->acc_rate = mci.getAcceptanceRate();
+        return 0;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 // Direct access to the reference estimators (include/mci/Estimators.hpp:9-45). nblocks is only used by BLOCK (=100).
 int mciref_estimate(int estim_type, int64_t n, int ndim, const double * x, int64_t nblocks, double * avg, double * err)
 {

@@ -98,6 +98,9 @@ RUNS = {
     "full_two_samples": dict(ndim=1, seed=81, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 1, 1, False, orc.EST_UNCORRELATED)], nmc=2, steps=(2.0,)),
     "vec_full_len": dict(ndim=3, seed=82, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=4096, move_type=orc.MOVE_VEC, veclen=3, steps=(0.9,)),
     "block_skip_big": dict(ndim=2, seed=83, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 64, 3, True, orc.EST_UNCORRELATED)], nmc=64*3*40, steps=(1.1,)),
+    # --- periodic text dumps (test/main.cpp:108-113 uses both with freq 100)
+    "dump_files": dict(ndim=3, seed=909, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XYZSQUARED, 4, 2), (orc.OBS_CONSTVAL, 0, 5)],
+                       nmc=4000, steps=(0.9,), x0=(0.2, -0.3, 0.4)),
     # --- no sampling function (plain MC over a box), ex_basic
     "nopdf_box": dict(ndim=3, seed=42, pdf_id=orc.PDF_NONE, obs=[(orc.OBS_GAUSSXSQUARED, 1, 1)], nmc=16384, lb=-5., ub=5.),
     "exbasic_1": dict(ndim=1, seed=7, pdf_id=orc.PDF_NONE, obs=[(orc.OBS_PARABOLA, 1, 1)], nmc=100000, lb=-1., ub=3., x0=(-0.5,), steps=(0.25,), target_acc=0.7,
@@ -105,6 +108,9 @@ RUNS = {
     "exbasic_2": dict(ndim=1, seed=7, pdf_id=orc.PDF_NORMLINE, obs=[(orc.OBS_NORMPARABOLA, 1, 1)], nmc=100000, lb=-1., ub=3., x0=(-0.5,), steps=(0.25,),
                       target_acc=0.7, do_find=True, do_decorr=True),
 }
+
+
+DUMP_OBS_FREQ, DUMP_WLK_FREQ = 100, 250
 
 
 def in_oracle(name):

@@ -199,3 +199,27 @@ def test_dynamic_equals_static_in_philox_mode(mcig):
         out.append((avg, err, wavg.copy(), werr.copy(), mci.getAcceptanceRate(), mci.getX(walker=999)))
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_file_dumps_match_reference_text(mcig, tmp_path):
+    """storeObservablesOnFile / storeWalkerPositionsOnFile (src/MCIntegrator.cpp:495-542): the text the device path writes for walker
+    0 in replay mode equals, character for character, what the reference wrote for the same run (tests/golden/dump_*.txt)."""
+    import os
+    spec = configs.RUNS["dump_files"]
+    mci = build_mci(mcig, spec)
+    op, wp = str(tmp_path / "observables.txt"), str(tmp_path / "walker.txt")
+    mci.storeObservablesOnFile(op, configs.DUMP_OBS_FREQ)
+    mci.storeWalkerPositionsOnFile(wp, configs.DUMP_WLK_FREQ)
+    avg, err = mci.integrate(spec["nmc"], False, False)
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    assert open(wp).read() == open(os.path.join(gold, "dump_walker.txt")).read()
+    assert open(op).read() == open(os.path.join(gold, "dump_observables.txt")).read()
+    # the dumps do not disturb the results, and can be switched off again
+    mci2 = build_mci(mcig, spec)
+    avg2, err2 = mci2.integrate(spec["nmc"], False, False)
+    assert np.array_equal(avg, avg2) and np.array_equal(err, err2)
+    mci.clearObservableFile()
+    mci.clearWalkerFile()
+    os.remove(op)
+    mci.integrate(100, False, False)
+    assert not os.path.exists(op)
