@@ -221,5 +221,5 @@ def test_file_dumps_match_reference_text(mcig, tmp_path):
     mci.clearObservableFile()
     mci.clearWalkerFile()
     os.remove(op)
-    mci.integrate(100, False, False)
+    mci.integrate(160, False, False)
     assert not os.path.exists(op)
