@@ -154,6 +154,11 @@ int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double 
 /* ---- engine knobs without reference analogue */
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
 int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory */
+/* findMRT2Step feedback loop on the device (default 1: sampling launch -> acceptance reduction -> controller kernel, no host
+ * synchronisation per iteration; used in the Philox modes of a single-process job) or on the host (0: one 8-byte readback per
+ * iteration; always used in replay mode and when a cross-process sum is installed). Same arithmetic, same results. */
+int mcig_set_device_calibration(mcig_ctx * ctx, int on);
+int mcig_get_calibration_iterations(mcig_ctx * ctx); /* iterations the last findMRT2Step executed */
 /* MCI::storeObservablesOnFile (what = 0) / storeWalkerPositionsOnFile (what = 1), src/MCIntegrator.cpp:495-542: text dump of
  * walker 0 every freq-th step of the main sampling run ("ridx v0 v1 ..."), written after the run from device-side shadow
  * accumulators. path NULL or "" switches the dump off (clearObservableFile / clearWalkerFile). */

@@ -506,6 +506,67 @@ __global__ void fcblocker_events_kernel(const double * __restrict__ data, i64 n,
     werr[col] = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
 }
 
+// ---------------------------------------------------------------------------------------------- device-resident calibration
+// Host mirror of mcig::CalibCtl (device/mcig_device.cuh) — keep both in sync.
+#define MCIG_CALIB_MAXTYPES 8
+struct CalibCtl {
+    double steps[MCIG_CALIB_MAXTYPES];
+    u64 group;
+    u64 acc;
+    int done, cons_count, counter, executed;
+};
+
+struct CalibArgs { // constants of one findMRT2Step call
+    double target;
+    double half_dim_size[MCIG_CALIB_MAXTYPES]; // min over the coordinates of a type of 0.5*domain size (upper clamp)
+    i64 steps_per_iter;  // MIN_STAT
+    i64 walkers;         // local walkers (acceptance counts are local: no cross-process sum on this path)
+    int ntypes;
+    int N;               // _NfindMRT2Iterations
+    int groups_per_step;
+};
+
+// acceptance counters -> ctl->acc (skipped once calibration is done)
+__global__ void calib_reduce_kernel(const u64 * __restrict__ nacc, i64 n, CalibCtl * __restrict__ ctl)
+{
+    if (ctl->done != 0) { return; }
+    __shared__ u64 sm[32];
+    u64 s = 0;
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) { s += nacc[i]; }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); }
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = s; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); }
+        if (threadIdx.x == 0) { ctl->acc = s; }
+    }
+}
+
+// The feedback rule of MCI::findMRT2Step (src/MCIntegrator.cpp:124-167), one iteration, one thread.
+__global__ void calib_controller_kernel(CalibCtl * __restrict__ ctl, const CalibArgs a)
+{
+    if (ctl->done != 0) { return; }
+    const double acc = (double)ctl->acc, rej = (double)(a.walkers*a.steps_per_iter) - acc;
+    const double rate = (ctl->acc > 0) ? acc/(acc + rej) : 0.; // getAcceptanceRate :587-592
+    int cons = ctl->cons_count;
+    if (fabs(rate - a.target) < 0.05) { ++cons; } else { cons = 0; } // TOLERANCE
+    const double fact = fmin(2., fmax(0.5, rate/a.target));
+    for (int t = 0; t < a.ntypes; ++t) {
+        double st = ctl->steps[t]*fact;
+        if (st > a.half_dim_size[t]) { st = a.half_dim_size[t]; }
+        if (st < 1.17549435082228750797e-38) { st = 1.17549435082228750797e-38; } // FLT_MIN
+        ctl->steps[t] = st;
+    }
+    const int counter = ctl->counter + 1;
+    ctl->cons_count = cons;
+    ctl->counter = counter;
+    ctl->executed += 1;
+    ctl->group += (u64)a.steps_per_iter*(u64)a.groups_per_step;
+    const bool again = ((a.N < 0 && cons < 5) || counter < a.N) && !(a.N < 0 && counter >= -a.N);
+    ctl->done = again ? 0 : 1;
+}
+
 // ready-queue of the dynamically scheduled walk kernel: chunk 0 of every walker block is ready, the rest is produced at run time
 __global__ void dyn_init_kernel(int * __restrict__ queue, int * __restrict__ ctrl, int nblocks, int total)
 {

@@ -198,3 +198,20 @@ def test_philox_rounds_option(mcig):
     assert not np.array_equal(out[10], out[7])
     with pytest.raises(McigError):
         build_mci(mcig, spec).setPhiloxRounds(3)
+
+
+@pytest.mark.parametrize("name", ["auto_default", "vec3_types", "ms_sub_ut5", "ut4_fixed"])
+def test_device_resident_calibration_equals_host_loop(name, mcig):
+    """findMRT2Step with the feedback rule applied by a controller kernel (no host round trip per iteration) must follow exactly
+    the trajectory of the host loop: same calibrated step sizes, same number of iterations, same Philox cursor afterwards
+    (hence bit-identical results of the following run)."""
+    spec = dict(configs.RUNS[name])
+    out = []
+    for on in (1, 0):
+        mci = build_mci(mcig, spec, nwalkers=2048, mode=0)
+        mci.setDeviceCalibration(on)
+        avg, err = mci.integrate(12288, True, False)
+        nt = max(1, spec.get("ntypes", 1))
+        out.append(([mci.getMRT2Step(i) for i in range(nt)], mci.getCalibrationIterations(), avg.copy(), err.copy(), mci.getAcceptanceRate()))
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1] and out[0][1] >= 1
+    assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3]) and out[0][4] == out[1][4]
