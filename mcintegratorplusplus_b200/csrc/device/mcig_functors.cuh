@@ -63,14 +63,14 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     template <class X, class P>
     MCIG_DEV void protoFunction(const X & in, P & pv) const
     {
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { pv[i] = in[i]*in[i]; }
     }
     template <class P>
     MCIG_DEV double samplingFunction(const P & pv) const
     {
         double s = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += pv[i]; }
         return exp(-s);
     }
@@ -78,9 +78,9 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return exp(a - b);
     }
@@ -88,9 +88,9 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return a - b;
     }
@@ -146,14 +146,14 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     template <class X, class P>
     MCIG_DEV void protoFunction(const X & in, P & pv) const
     {
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { pv[i] = fabs(in[i]); }
     }
     template <class P>
     MCIG_DEV double samplingFunction(const P & pv) const
     {
         double s = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += pv[i]; }
         return exp(-s);
     }
@@ -161,9 +161,9 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return exp(a - b);
     }
@@ -171,9 +171,9 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return a - b;
     }
@@ -266,7 +266,7 @@ struct XND { // TestMCIFunctions.hpp:339-379 (XND and UpdateableXND compute the 
     template <class X, class O>
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { out[i] = in[i]; }
     }
 };
@@ -286,7 +286,7 @@ struct Polynom { // TestMCIFunctions.hpp:401-420
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
         double s = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += in[i]; }
         out[0] = s;
     }
@@ -300,7 +300,7 @@ struct X2Sum { // TestMCIFunctions.hpp:423-442
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
         double s = 0.;
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += in[i]*in[i]; }
         out[0] = s;
     }
@@ -313,7 +313,7 @@ struct X2 { // TestMCIFunctions.hpp:445-473
     template <class X, class O>
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
-#pragma unroll
+#pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { out[i] = in[i]*in[i]; }
     }
 };

@@ -16,10 +16,10 @@
 extern "C" {
 #endif
 
-#define ORC_MAXDIM 64
+#define ORC_MAXDIM 1024
 #define ORC_MAXOBS 8
 #define ORC_MAXTYPES 8
-#define ORC_MAXOBSDIM 256
+#define ORC_MAXOBSDIM 2048
 
 /* sampling functions (reference file:line) */
 enum {

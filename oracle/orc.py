@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-MAXDIM, MAXOBS, MAXTYPES, MAXOBSDIM = 64, 8, 8, 256
+MAXDIM, MAXOBS, MAXTYPES, MAXOBSDIM = 1024, 8, 8, 2048
 
 PDF_NONE, PDF_GAUSS3D, PDF_GAUSS, PDF_EXP1D, PDF_EXPND, PDF_NORMLINE = range(6)
 (OBS_XSQUARED, OBS_GAUSSXSQUARED, OBS_XYZSQUARED, OBS_X1D, OBS_XND, OBS_UPDXND, OBS_CONSTVAL, OBS_POLYNOM,

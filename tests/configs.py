@@ -57,6 +57,19 @@ RUNS = {
     "ndim_all64": dict(ndim=64, seed=4242, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 8, 1)], nmc=8192, steps=(0.12,), x0=_alt(64)),
     "ndim_vec64_v4": dict(ndim=64, seed=4242, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 4), (orc.OBS_XND, 0, 1)], nmc=16384, move_type=orc.MOVE_VEC,
                           veclen=4, steps=(0.6,), x0=_alt(64)),
+    # --- walkers beyond the register / shared-memory budget (the reference's dimension sweeps go to 1024): streamed all-move
+    #     draws above 64 coordinates, global-memory state placement once a warp of walkers exceeds 227 KiB of shared memory
+    "ndim_all96": dict(ndim=96, seed=11, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 8, 1), (orc.OBS_XND, 0, 1)], nmc=2048, steps=(0.1,), x0=_alt(96)),
+    "ndim_gauss_all96": dict(ndim=96, seed=12, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1)], nmc=2048, srrd=orc.SRRD_GAUSSIAN, steps=(0.06,), x0=_alt(96)),
+    "ndim_vec256": dict(ndim=256, seed=13, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1), (orc.OBS_UPDXND, 8, 2)], nmc=4096, move_type=orc.MOVE_VEC, veclen=1,
+                        steps=(1.2,), x0=_alt(256)),
+    "ndim_vec300_v3_types": dict(ndim=300, seed=14, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 0, 1)], nmc=4096, move_type=orc.MOVE_VEC, veclen=3, ntypes=2,
+                                 type_ends=[150, 300], steps=(2.0, 1.0), x0=_alt(300), lb=-8., ub=8., nfind=-20, ndecorr=-2000, do_find=True, do_decorr=True),
+    "ndim_all300": dict(ndim=300, seed=15, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 16, 1), (orc.OBS_X2SUM, 1, 1)], nmc=1024, steps=(0.05,), x0=_alt(300)),
+    "ndim_ms256": dict(ndim=256, seed=16, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=400, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.2,),
+                       x0=_alt(256)),
+    "ndim_all1024": dict(ndim=1024, seed=17, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_X2SUM, 4, 1)], nmc=256, steps=(0.03,), x0=_alt(1024)),
+    "ndim_vec1024": dict(ndim=1024, seed=18, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 8)], nmc=4096, move_type=orc.MOVE_VEC, veclen=2, steps=(1.0,), x0=_alt(1024)),
     # --- MultiStepMove
     "ms_default4": dict(ndim=4, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1)], nmc=50000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.7,)),
     "ms_sub_ut5": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_X2, 1, 3)], nmc=32768*3, move_type=orc.MOVE_MULTISTEP,

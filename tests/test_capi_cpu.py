@@ -99,15 +99,23 @@ def test_no_cpu_fallback(mcig):
         mcig.measure_peaks()
 
 
-def test_oversized_walker_fails_with_a_clear_message(mcig):
-    """One chain per thread keeps the walker on chip; a walker that cannot fit must be refused loudly, not crash at launch."""
+def test_state_placement_follows_the_walker_size(mcig):
+    """One chain per thread keeps the walker on chip while it fits (registers, then shared memory); beyond 227 KiB per warp of
+    walkers the state moves to global memory automatically. Forcing shared memory for such a walker is refused loudly."""
     from mcintegratorplusplus_b200._capi import McigError
-    mci = mcig.MCI(512)
-    mci.addSamplingFunction(mcig.Gauss(512))
-    mci.addObservable(mcig.X2Sum(512), 0, 1)
-    with pytest.raises(McigError, match="shared memory"):
+
+    def make(ndim, placement=None):
+        mci = mcig.MCI(ndim)
+        mci.addSamplingFunction(mcig.Gauss(ndim))
+        mci.addObservable(mcig.X2Sum(ndim), 0, 1)
+        if placement is not None:
+            mci.setStatePlacement(placement)
         mci.prebuild()
-    ok = mcig.MCI(128)  # 131 KiB per warp of walkers: fits
-    ok.addSamplingFunction(mcig.Gauss(128))
-    ok.addObservable(mcig.X2Sum(128), 0, 1)
-    ok.prebuild()
+        return mci.kernelSource()
+
+    assert "walk_kernel_reg" in make(3)
+    assert "walk_kernel_smem" in make(128)  # 131 KiB per warp of walkers: fits
+    assert "walk_kernel_gmem" in make(512)
+    assert "walk_kernel_gmem" in make(3, placement=2)
+    with pytest.raises(McigError, match="shared memory"):
+        make(512, placement=1)

@@ -51,10 +51,10 @@ def test_replay_vs_oracle_and_golden(name, mcig, oracle, golden_runs):
     assert _close(err, ref["err"], ERR_RTOL, atol=1e-18), (err, ref["err"])
 
 
-@pytest.mark.parametrize("placement", [0, 1])
+@pytest.mark.parametrize("placement", [0, 1, 2])
 @pytest.mark.parametrize("name", ["c1_simple_short", "vec_exp4", "ms_default4", "ms_sub_ut5", "all_types", "vec3_types"])
 def test_register_and_smem_paths_agree(name, placement, mcig, oracle):
-    """Both state placements (registers / shared memory) must reproduce the oracle."""
+    """All state placements (registers / shared memory / global memory) must reproduce the oracle."""
     spec = configs.RUNS[name]
     ref = oracle.run(configs.make(name))
     mci = build_mci(mcig, spec, placement=placement)
@@ -223,3 +223,55 @@ def test_file_dumps_match_reference_text(mcig, tmp_path):
     os.remove(op)
     mci.integrate(160, False, False)
     assert not os.path.exists(op)
+
+
+@pytest.mark.parametrize("name", ["ndim_all64", "ndim_vec64_v4", "gauss_vec6_v3", "ms_sub16", "vec_ortho_types", "ndim_all96"])
+def test_global_memory_placement_equals_shared_memory_in_philox_mode(name, mcig):
+    """The global-memory state placement runs the same code over a different view: production-mode results must be bit-identical."""
+    spec = configs.RUNS[name]
+    out = []
+    for placement in (1, 2):
+        mci = build_mci(mcig, spec, nwalkers=96, mode=0, placement=placement)
+        avg, err = mci.integrate(spec["nmc"], False, False)
+        out.append((avg.copy(), err.copy(), mci.getAcceptanceRate(), list(mci.getX())))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2:] == out[1][2:]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["ndim_all64", "gauss_all", "srrd_exponential_all", "srrd_lognormal_all", "srrd_student_all"])
+def test_streamed_draws_equal_register_draws(name, mode, mcig, monkeypatch):
+    """All-moves over more than MCIG_STREAM_NDIM coordinates generate their Philox blocks on demand instead of holding every draw in
+    registers. Same (group, walker, block) -> word mapping: lowering the threshold must not change a single bit, for any distribution."""
+    spec = dict(configs.RUNS[name])
+    out = []
+    for defs in ("", "MCIG_STREAM_NDIM=1"):
+        if defs:
+            monkeypatch.setenv("MCIG_JIT_DEFINES", defs)
+        else:
+            monkeypatch.delenv("MCIG_JIT_DEFINES", raising=False)
+        mci = build_mci(mcig, spec, nwalkers=64, mode=mode, placement=1)
+        avg, err = mci.integrate(2048, False, False)
+        out.append((avg.copy(), err.copy(), mci.getAcceptanceRate(), list(mci.getX())))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2:] == out[1][2:]
+    assert 0.02 < out[0][2] < 0.99
+
+
+def test_thousand_dimensional_walkers_sample_the_right_distribution(mcig):
+    """ndim = 1024 (the top of the reference's dimension sweeps, benchmark/bench_throughput_ndim_*): single-particle moves over
+    global-memory walkers; <x_i^2> of the unit-variance-1/2 Gaussian is 0.5 for every coordinate (test/common/TestMCIFunctions.hpp)."""
+    nd = 1024
+    mci = mcig.MCI(nd)
+    mci.setRngMode(0)
+    mci.setNWalkers(2048)
+    mci.setSeed(1337)
+    mci.setTrialMove(mcig.SRRDType.Uniform, 1, 1, None)
+    mci.setMRT2Step(0, 1.6)
+    mci.setX([0.0]*nd)
+    mci.addSamplingFunction(mcig.Gauss(nd))
+    mci.addObservable(mcig.X2(nd), 0, 1)
+    mci.integrate(20*nd, False, False)  # ~20 sweeps to equilibrate
+    avg, _ = mci.integrate(40*nd, False, False)
+    assert 0.3 < mci.getAcceptanceRate() < 0.7
+    # 2048 walkers x 40 sweeps of correlated samples per coordinate: standard error ~ 0.5*sqrt(2)/sqrt(2048*40/4) ~ 0.005
+    assert avg.shape == (nd,) and np.all(np.abs(avg - 0.5) < 0.03), (avg.min(), avg.max())
+    assert abs(avg.mean() - 0.5) < 2e-3
