@@ -147,6 +147,9 @@ int mcig_get_obs_data(mcig_ctx * ctx, int iobs, int64_t walker, double * data);
 /* device times of the last integrate in ms (CUDA events on the engine's stream): the walk kernel of the main sampling run,
  * the estimation stage, the whole call (calibration + decorrelation + sampling + estimation); and the kernels it launched */
 int mcig_get_timings(mcig_ctx * ctx, double * walk_ms, double * estim_ms, double * total_ms, int64_t * kernel_launches);
+/* host-clock phases of the last integrate in ms: findMRT2Step, initialDecorrelation, and run-time compilation / module loads
+ * (first use of a configuration; contained in whichever phase triggered them) */
+int mcig_get_phase_timings(mcig_ctx * ctx, double * find_ms, double * decorr_ms, double * jit_ms);
 
 /* ---- estimators on host data (include/mci/Estimators.hpp:9-45): data x[n][ndim], run on the device */
 int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double * average, double * error);

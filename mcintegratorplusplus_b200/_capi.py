@@ -58,6 +58,7 @@ SIGNATURES = {
     "mcig_get_nstore": (C.c_int64, [_ctx, C.c_int]),
     "mcig_get_obs_data": (C.c_int, [_ctx, C.c_int, C.c_int64, _dp]),
     "mcig_get_timings": (C.c_int, [_ctx, _dp, _dp, _dp, _i64p]),
+    "mcig_get_phase_timings": (C.c_int, [_ctx, _dp, _dp, _dp]),
     "mcig_estimate": (C.c_int, [C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp]),
     "mcig_set_block_size": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_state_placement": (C.c_int, [_ctx, C.c_int]),

@@ -314,7 +314,9 @@ class MCI:
     def timings(self):
         w, e, t, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         _capi.check(self._lib.mcig_get_timings(self._ctx, C.byref(w), C.byref(e), C.byref(t), C.byref(n)))
-        return {"walk_ms": w.value, "estim_ms": e.value, "total_ms": t.value, "launches": n.value}
+        f, d, j = C.c_double(), C.c_double(), C.c_double()
+        _capi.check(self._lib.mcig_get_phase_timings(self._ctx, C.byref(f), C.byref(d), C.byref(j)))
+        return {"walk_ms": w.value, "estim_ms": e.value, "total_ms": t.value, "launches": n.value, "find_ms": f.value, "decorr_ms": d.value, "jit_ms": j.value}
 
     def setBlockSize(self, n): _capi.check(self._lib.mcig_set_block_size(self._ctx, int(n)))
     def setStatePlacement(self, p): _capi.check(self._lib.mcig_set_state_placement(self._ctx, int(p)))

@@ -79,15 +79,16 @@ def c5_mixed(W=65536, nmc=100000):
     mci.addObservable(m.XSquared(), 1, 5)
     mci.addObservable(m.XYZSquared(), 5, 2)
     mci.setMRT2Step(1.0)
-    for auto in (False, True):
+    for auto in (False, True, True):  # the first automatic run compiles / loads the calibration and equilibration kernel variants
         mci.integrate(1000, False, False)
+        mci.setMRT2Step(1.0)
         t0 = time.perf_counter()
         avg, err = mci.integrate(nmc, auto, auto)
         wall = time.perf_counter() - t0
         t = mci.timings()
         print(json.dumps({"config": "C5_mixed", "auto_calibration_decorrelation": auto, "walkers": W, "nmc": nmc, "samples_per_s_total": W*nmc/(t["total_ms"]*1e-3),
-                          "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "total_ms": t["total_ms"], "wall_ms": 1e3*wall, "launches": t["launches"],
-                          "step": mci.getMRT2Step(0), "acceptance": mci.getAcceptanceRate(), "avg": [float(v) for v in avg], "err": [float(v) for v in err]}), flush=True)
+                          "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "total_ms": t["total_ms"], "wall_ms": 1e3*wall, "launches": t["launches"], "find_ms": t["find_ms"], "decorr_ms": t["decorr_ms"], "jit_ms": t["jit_ms"],
+                          "calibration_iterations": mci.getCalibrationIterations(), "step": mci.getMRT2Step(0), "acceptance": mci.getAcceptanceRate(), "avg": [float(v) for v in avg], "err": [float(v) for v in err]}), flush=True)
 
 
 if __name__ == "__main__":
@@ -96,6 +97,10 @@ if __name__ == "__main__":
         c3_ndim("vec")
         c3_ndim("all")
         c3_ndim("multistep", ndims=(2, 4, 8, 16, 32))
+    if "c3big" in which:  # the upper half of the reference's dimension sweeps (benchmark/bench_throughput_ndim_*: up to 1024)
+        c3_ndim("vec", ndims=(128, 256, 512, 1024), W=16384, nmc=20000)
+        c3_ndim("all", ndims=(128, 256, 512, 1024), W=16384, nmc=2000)
+        c3_ndim("multistep", ndims=(64, 128, 256), W=16384, nmc=200)
     if "c4" in which:
         c4_estimators()
     if "c5" in which:
