@@ -445,6 +445,128 @@ __global__ void fcblocker_kernel(const double * __restrict__ data, i64 n, i64 nc
 // Block sums obtained as prefix differences differ from the reference's direct sums by O(1e-16 * |prefix|/|block sum|)
 // relative — far inside the 1e-9 estimator tolerance; series up to MCIG_FC_EXACT_MAX samples use the exact kernel above.
 #define MCIG_FC_EXACT_MAX 4096
+__device__ __forceinline__ double fc_tree16(const double * v)
+{ // pairwise sum: dependency depth 4 instead of 16 (the running sum is a latency chain: one thread per chain, few warps per SM)
+    const double a0 = __dadd_rn(v[0], v[1]), a1 = __dadd_rn(v[2], v[3]), a2 = __dadd_rn(v[4], v[5]), a3 = __dadd_rn(v[6], v[7]);
+    const double a4 = __dadd_rn(v[8], v[9]), a5 = __dadd_rn(v[10], v[11]), a6 = __dadd_rn(v[12], v[13]), a7 = __dadd_rn(v[14], v[15]);
+    return __dadd_rn(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)), __dadd_rn(__dadd_rn(a4, a5), __dadd_rn(a6, a7)));
+}
+
+// Stream rows [r0, r1) of one chain into the running sum, 16 loads in flight whether or not a block border falls inside the batch
+// (short series have a border every ~n/1260 samples: a loop that stops at every border would issue one load at a time).
+// on_border(run) is called after the sample that completes the prefix [0, next) and must advance `next`.
+template <class OnBorder>
+__device__ __forceinline__ void fc_stream(const double * __restrict__ src, i64 ncol, i64 r0, i64 r1, i64 & next, double & run, OnBorder && on_border)
+{
+    i64 i = r0;
+    for (; i + 16 <= r1; i += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { v[u] = __ldcs(src + (i + u)*ncol); }
+        if (next > i + 16) { run = __dadd_rn(run, fc_tree16(v)); }
+        else {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                run = __dadd_rn(run, v[u]);
+                if (i + u + 1 == next) { on_border(run); }
+            }
+        }
+    }
+    for (; i < r1; ++i) {
+        run = __dadd_rn(run, __ldcs(src + i*ncol));
+        if (i + 1 == next) { on_border(run); }
+    }
+}
+
+// Statistics of the 45 partitions -> plateau search -> 5-point averages (src/Estimators.cpp:82-122, 191-246)
+__device__ __forceinline__ void fc_finish(const double * s1, const double * s2, int nobs_is_one, double & out_avg, double & out_err)
+{
+    constexpr int MINB = 6, MAXB = 50, NAV = MAXB - MINB + 1, MPA = 4, NACCD = NAV - 2*MPA;
+    double av[NAV], err[NAV];
+    for (int a = 0; a < NAV; ++a) {
+        const double nb = (double)(a + MINB);
+        const double norm = 1./nb;
+        const double mean = __dmul_rn(s1[a], norm);
+        double er = __dadd_rn(__dmul_rn(s2[a], norm), -__dmul_rn(mean, mean));
+        if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/(nb - 1.)) : sqrt(__dmul_rn(er, 1./(nb - 1.))); }
+        else { er = 0.; }
+        av[a] = mean;
+        err[a] = er;
+    }
+    double accd[NACCD];
+    for (int i2 = MPA; i2 < NACCD + MPA; ++i2) {
+        double acc = 0.;
+        for (int i1 = 1; i1 <= MPA; ++i1) { acc = __dadd_rn(acc, fc_err_delta(i1, err + i2)); }
+        accd[i2 - MPA] = acc;
+    }
+    int imin = 0;
+    for (int i2 = 1; i2 < NACCD; ++i2) {
+        if (fabs(accd[i2]) < fabs(accd[imin])) { imin = i2; }
+    }
+    imin += MPA;
+    out_avg = 0.2*(av[imin - 2] + av[imin - 1] + av[imin] + av[imin + 1] + av[imin + 2]);
+    out_err = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
+}
+
+// Few long chains (ncol threads would leave the GPU empty): split every chain into nseg time segments. Pass 1 streams segment
+// (seg, col) and records the LOCAL running sum at every block border inside it plus the segment total; pass 2 walks the <= 1260
+// events of a chain in order with global prefix = (sum of earlier segment totals) + local prefix.
+__global__ void fc_split_prefix_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nseg, const i64 * __restrict__ ev_pos, int nev,
+                                       double * __restrict__ ev_prefix /*[nev][ncol]*/, double * __restrict__ seg_total /*[nseg][ncol]*/)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    const int seg = (int)blockIdx.y;
+    if (col >= ncol) { return; }
+    const i64 len = (n + nseg - 1)/nseg;
+    const i64 r0 = (i64)seg*len;
+    const i64 r1 = (r0 + len < n) ? r0 + len : n;
+    // first event with position > r0 (events at r0 belong to the previous segment: their prefix excludes row r0)
+    int lo = 0, hi = nev;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ev_pos[mid] > r0) { hi = mid; }
+        else { lo = mid + 1; }
+    }
+    int e = lo;
+    i64 next = (e < nev) ? ev_pos[e] : n + 1;
+    double run = 0.;
+    fc_stream(data + col, ncol, r0, r1, next, run, [&](double r) {
+        const i64 pos = next;
+        while (next == pos) {
+            ev_prefix[(i64)e*ncol + col] = r;
+            ++e;
+            next = (e < nev) ? ev_pos[e] : n + 1;
+        }
+    });
+    seg_total[(i64)seg*ncol + col] = run;
+}
+
+__global__ void fc_split_finish_kernel(i64 n, i64 ncol, int nseg, int nobs_is_one, const i64 * __restrict__ ev_pos, const int * __restrict__ ev_part, int nev,
+                                       const double * __restrict__ ev_prefix, const double * __restrict__ seg_total, double * __restrict__ wavg,
+                                       double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    constexpr int MINB = 6, NAV = 45;
+    double last[NAV], s1[NAV], s2[NAV];
+    for (int a = 0; a < NAV; ++a) { last[a] = 0.; s1[a] = 0.; s2[a] = 0.; }
+    const i64 len = (n + nseg - 1)/nseg;
+    double base = 0.;
+    int seg = 0;
+    for (int e = 0; e < nev; ++e) {
+        const i64 pos = ev_pos[e];
+        const int sg = (int)((pos - 1)/len); // segment holding row pos-1, the last row inside the prefix
+        while (seg < sg) { base = __dadd_rn(base, seg_total[(i64)seg*ncol + col]); ++seg; }
+        const double run = __dadd_rn(base, ev_prefix[(i64)e*ncol + col]);
+        const int a = ev_part[e];
+        const double nper = (double)(n/(a + MINB));
+        const double av = __dmul_rn(__dadd_rn(run, -last[a]), 1./nper);
+        last[a] = run;
+        s1[a] = __dadd_rn(s1[a], av);
+        s2[a] = __dadd_rn(s2[a], __dmul_rn(av, av));
+    }
+    fc_finish(s1, s2, nobs_is_one, wavg[col], werr[col]);
+}
 __global__ void fcblocker_events_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, const i64 * __restrict__ ev_pos,
                                         const int * __restrict__ ev_part, int nev, double * __restrict__ wavg, double * __restrict__ werr)
 {
@@ -456,30 +578,21 @@ __global__ void fcblocker_events_kernel(const double * __restrict__ data, i64 n,
     double run = 0.;
     int e = 0;
     i64 next = (nev > 0) ? ev_pos[0] : n + 1;
-    const double * src = data + col;
-    i64 i = 0;
-    while (i < n) {
-        const i64 stop = (next < n) ? next : n; // stream up to the next block border
-        for (; i + 16 <= stop; i += 16) {
-            double v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) { v[u] = __ldcs(src + (i + u)*ncol); }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) { run = __dadd_rn(run, v[u]); }
-        }
-        for (; i < stop; ++i) { run = __dadd_rn(run, __ldcs(src + i*ncol)); }
-        while (i == next) { // a block of partition a ends after sample i-1
+    // rows after the last block border are ignored by every partition (Estimators.cpp:65, :164)
+    const i64 last_border = (nev > 0) ? ev_pos[nev - 1] : 0;
+    fc_stream(data + col, ncol, 0, last_border, next, run, [&](double r) {
+        const i64 pos = next;
+        while (next == pos) { // a block of partition a ends after sample pos-1
             const int a = ev_part[e];
             const double nper = (double)(n/(a + MINB));
-            const double av = __dmul_rn(__dadd_rn(run, -last[a]), 1./nper);
-            last[a] = run;
+            const double av = __dmul_rn(__dadd_rn(r, -last[a]), 1./nper);
+            last[a] = r;
             s1[a] = __dadd_rn(s1[a], av);
             s2[a] = __dadd_rn(s2[a], __dmul_rn(av, av));
             ++e;
             next = (e < nev) ? ev_pos[e] : n + 1;
         }
-        if (e >= nev) { break; } // the remainder after the last block border is ignored by every partition (Estimators.cpp:65, :164)
-    }
+    });
     double av[NAV], err[NAV];
     for (int a = 0; a < NAV; ++a) {
         const double nb = (double)(a + MINB);

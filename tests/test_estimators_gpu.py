@@ -45,6 +45,25 @@ def test_mjblocker_large_power_of_two_segments(mcig, oracle):
     assert np.all(err > 2*err_u)  # blocking must see the correlation
 
 
+def test_fcblocker_long_chains_time_split(mcig, oracle):
+    """Few long chains whose length is not a power of two (the default estimator then is the FCBlocker, src/Estimators.cpp:278-286):
+    the chains are split in time, block sums come from prefix differences across segments. Against the oracle's direct block sums."""
+    rng = np.random.default_rng(11)
+    n = 3*(1 << 19) + 17
+    e = rng.normal(size=(n, 2))
+    x = np.empty_like(e)
+    x[0] = e[0]
+    for i in range(1, n):
+        x[i] = 0.8*x[i - 1] + e[i] + 0.25
+    for data in (x, x[:, 0].copy(), x[:100003]):
+        avg_o, err_o = oracle.estimate(orc.EST_FCBLOCKER, data)
+        avg, err = mcig.estimate(orc.EST_FCBLOCKER, data)
+        assert np.allclose(avg, avg_o, rtol=1e-12, atol=1e-15), (avg, avg_o)
+        assert np.allclose(err, err_o, rtol=1e-9), (err, err_o)
+        avg_c, err_c = mcig.estimate(orc.EST_CORRELATED, data)  # dispatches to the FCBlocker: n is not a power of two
+        assert np.array_equal(avg_c, avg) and np.array_equal(err_c, err)
+
+
 def test_constant_series_defined_error(mcig, oracle):
     """Constval-like data (test/main.cpp:82-88). An exactly representable constant has zero variance at every level: the
     reference then reads out of bounds; here and in the oracle err is defined as 0. A constant

@@ -67,6 +67,13 @@ def c4_estimators(W=65536, npow=14):
         wall = time.perf_counter() - t0
     print(json.dumps({"config": "C4_single_chain_2^27", "estimator": "MJBlocker", "wall_ms_incl_1GiB_H2D": 1e3*wall, "avg": float(avg[0]), "err": float(err[0]),
                       "expected_err": float(1/np.sqrt(n))}), flush=True)
+    for label, est, xs in (("FCBlocker", m.EstimatorType.FCBlocker, x[:n - 1]), ("Uncorrelated", m.EstimatorType.Uncorrelated, x)):
+        for i in range(0, 2):
+            t0 = time.perf_counter()
+            avg, err = m.estimate(est, xs)
+            wall = time.perf_counter() - t0
+        print(json.dumps({"config": "C4_single_chain_2^27", "estimator": label, "n": int(len(xs)), "wall_ms_incl_1GiB_H2D": 1e3*wall, "avg": float(avg[0]),
+                          "err": float(err[0]), "expected_err": float(1/np.sqrt(n))}), flush=True)
 
 
 def c5_mixed(W=65536, nmc=100000):
