@@ -40,6 +40,7 @@ struct DeviceFunctor
     bool hasUpdate = false;     // functor overrides updatedAcceptance
     bool elementwise = false;   // proto value k depends on x[k] only
     bool logAcceptance = false; // functor provides logAcceptance(protoold, protonew)
+    bool dependent = false;     // observable functor takes observableFunction(x, out, dep) (mci::DependentObservableInterface)
 
     DeviceFunctor() = default;
     explicit DeviceFunctor(std::string registeredName, std::vector<double> par = {}): name(std::move(registeredName)), params(std::move(par)) {}
@@ -50,7 +51,8 @@ struct DeviceFunctor
     int resolve(int kind, int ndim, int nvalues) const
     {
         if (!typeExpr.empty()) {
-            const int flags = (hasUpdate ? MCIG_PLUGIN_HAS_UPDATE : 0) | (elementwise ? MCIG_PLUGIN_ELEMENTWISE : 0) | (logAcceptance ? MCIG_PLUGIN_LOG_ACCEPTANCE : 0);
+            const int flags = (hasUpdate ? MCIG_PLUGIN_HAS_UPDATE : 0) | (elementwise ? MCIG_PLUGIN_ELEMENTWISE : 0) | (logAcceptance ? MCIG_PLUGIN_LOG_ACCEPTANCE : 0) |
+                              (dependent ? MCIG_PLUGIN_DEPENDENT : 0);
             const int id = mcig_register_plugin(kind, name.c_str(), typeExpr.c_str(), source.c_str(), ndim, nvalues, static_cast<int>(params.size()), flags);
             if (id < 0) { detail::check(-id); }
             return id;

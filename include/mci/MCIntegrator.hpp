@@ -6,15 +6,18 @@
 //   * setNWalkers(W): one MCI runs W independent chains ("virtual MPI ranks", src/MPIMCI.cpp:83); W defaults to 1.
 //     integrate() returns the MPIMCI combination over walkers (avg of per-walker averages, sqrt(sum err^2)/W).
 //   * setRngMode(): Philox4x32-10 in registers (default) or replay of per-walker std::mt19937_64 streams (bit-exact parity).
-//   * setCallback is not available: a per-step host callback cannot exist in a device-resident loop.
+//   * setCallback takes a device functor (mci/StepCallbackInterface.hpp) instead of a host std::function; dependent observables
+//     get their dependencies as a functor argument (mci/DependentObservableInterface.hpp).
 //     storeObservablesOnFile / storeWalkerPositionsOnFile work (walker 0, written after the run).
 #ifndef MCIG_MCI_MCINTEGRATOR_HPP
 #define MCIG_MCI_MCINTEGRATOR_HPP
 
+#include "mci/DependentObservableInterface.hpp"
 #include "mci/DomainInterface.hpp"
 #include "mci/Factories.hpp"
 #include "mci/ObservableFunctionInterface.hpp"
 #include "mci/SamplingFunctionInterface.hpp"
+#include "mci/StepCallbackInterface.hpp"
 #include "mci/TrialMoveInterface.hpp"
 
 #include <cstdint>
@@ -49,7 +52,9 @@ private:
     int _NfindMRT2Iterations{-50};      // src/MCIntegrator.cpp:638
     int64_t _NdecorrelationSteps{-10000}; // :639
     double _targetaccrate{0.5};         // :637
-    bool _dirtyMove{true}, _dirtyPdf{true}, _dirtyObs{true}, _dirtyDomain{true};
+    bool _dirtyMove{true}, _dirtyPdf{true}, _dirtyObs{true}, _dirtyDomain{true}, _dirtyCback{false};
+    std::unique_ptr<StepCallbackInterface> _cback; // device-functor replacement of the reference's std::function _cback
+    int64_t _cbackDoubles{0};
     std::mt19937_64 _hostgen; // only for newRandomX()/moveX() (manual position helpers)
 
     static int toSrrd(SRRDType t)
@@ -97,11 +102,24 @@ private:
         if (_dirtyObs) {
             detail::check(mcig_clear_obs(_ctx));
             for (auto & el : _obs) {
-                const DeviceFunctor f = el.obs->deviceFunctor();
+                DeviceFunctor f = el.obs->deviceFunctor();
+                if (dynamic_cast<const DependentObservableInterface *>(el.obs.get()) != nullptr) { f.dependent = true; }
                 detail::check(mcig_add_obs(_ctx, f.resolve(MCIG_PLUGIN_OBS, el.obs->getNDim(), el.obs->getNObs()), f.params.data(), static_cast<int>(f.params.size()),
                                            el.blocksize, el.nskip, el.flag_equil ? 1 : 0, static_cast<int>(el.estimType)));
             }
             _dirtyObs = false;
+        }
+        if (_dirtyCback) {
+            if (_cback) {
+                const DeviceFunctor f = _cback->deviceFunctor();
+                _cbackDoubles = _cback->bufferDoubles(mcig_get_walkers(_ctx));
+                detail::check(mcig_set_callback(_ctx, f.resolve(MCIG_PLUGIN_CALLBACK, 0, 0), f.params.data(), static_cast<int>(f.params.size()), _cbackDoubles));
+            }
+            else {
+                _cbackDoubles = 0;
+                detail::check(mcig_clear_callback(_ctx));
+            }
+            _dirtyCback = false;
         }
         detail::check(mcig_set_autotune(_ctx, _NfindMRT2Iterations, _NdecorrelationSteps, _targetaccrate));
     }
@@ -278,9 +296,28 @@ public:
         _dirtyPdf = true;
     }
 
-    // --- per-step host callbacks are not available on the device path (see header comment)
-    void setCallback(const std::function<void(const MCI &)> &) { throw std::logic_error("[MCI::setCallback] per-step host callbacks are not available in the device-resident walk"); }
-    void clearCallback() {}
+    // --- Callback: a device functor called after every move (see mci/StepCallbackInterface.hpp). A host std::function cannot run
+    // inside a kernel: that overload throws and names the replacement.
+    void setCallback(const StepCallbackInterface & cback)
+    {
+        _cback = cback.clone();
+        _dirtyCback = true;
+    }
+    void setCallback(const std::function<void(const MCI &)> &)
+    {
+        throw std::logic_error("[MCI::setCallback] a host callback cannot run inside the device-resident walk: pass a mci::StepCallbackInterface (device functor)");
+    }
+    void clearCallback()
+    {
+        _cback.reset();
+        _dirtyCback = true;
+    }
+    std::vector<double> getCallbackBuffer() const
+    {
+        std::vector<double> out(static_cast<size_t>(_cbackDoubles));
+        detail::check(mcig_get_callback_buffer(_ctx, out.data(), _cbackDoubles));
+        return out;
+    }
     // file dumps of walker 0 every freq-th step (src/MCIntegrator.cpp:495-542), written after the run from device-side accumulators
     void storeObservablesOnFile(const std::string & filepath, int freq) { detail::check(mcig_store_on_file(_ctx, 0, filepath.c_str(), freq)); }
     void clearObservableFile() { detail::check(mcig_store_on_file(_ctx, 0, "", 0)); }
@@ -322,6 +359,7 @@ public:
     void setNWalkers(int64_t nwalkers, int64_t globalOffset = 0, int64_t totalWalkers = -1)
     {
         detail::check(mcig_set_walkers(_ctx, nwalkers, globalOffset, totalWalkers < 0 ? nwalkers + globalOffset : totalWalkers));
+        _dirtyCback = (_cback != nullptr) || _dirtyCback; // its buffer is sized by the walker count
     }
     int64_t getNWalkers() const { return mcig_get_walkers(_ctx); }
     void setRngMode(RngMode mode) { detail::check(mcig_set_rng_mode(_ctx, static_cast<int>(mode))); }

@@ -47,12 +47,13 @@ enum {
     MCIG_RNG_REPLAY = 2    /* per-walker std::mt19937_64 + libstdc++ distributions generated on the host and consumed by
                               the kernel in the reference's order: bit-exact reference trajectories (parity mode) */
 };
-enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1 };
+enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1, MCIG_PLUGIN_CALLBACK = 2 };
 /* plugin flags (sampling functions) */
 enum {
     MCIG_PLUGIN_HAS_UPDATE = 1,     /* functor overrides updatedAcceptance (selective update for single-vector moves) */
     MCIG_PLUGIN_ELEMENTWISE = 2,    /* proto value k depends on x[k] only; updatedAcceptance touches protonew[changedIdx] only */
-    MCIG_PLUGIN_LOG_ACCEPTANCE = 4  /* functor provides logAcceptance(protoold, protonew) = log(acceptanceFunction) */
+    MCIG_PLUGIN_LOG_ACCEPTANCE = 4, /* functor provides logAcceptance(protoold, protonew) = log(acceptanceFunction) */
+    MCIG_PLUGIN_DEPENDENT = 8       /* observable: observableFunction(x, out, dep) with dep.proto(i) / dep.obs(k, j) (DependentObservableInterface) */
 };
 
 const char * mcig_last_error(void);
@@ -117,6 +118,18 @@ int mcig_add_obs(mcig_ctx * ctx, int plugin_id, const double * par, int npar, in
 int mcig_pop_obs(mcig_ctx * ctx);
 int mcig_clear_obs(mcig_ctx * ctx);
 int mcig_get_nobsdim(mcig_ctx * ctx);
+
+/* ---- MCI::setCallback / clearCallback  include/mci/MCIntegrator.hpp:186-190, called at src/MCIntegrator.cpp:346 and :374 after every
+ *      move (in every sampling run: calibration, decorrelation, main), after the accept decision and before the state is committed.
+ *      The reference's std::function<void(const MCI &)> runs host code inside the step loop; here the callback is a __device__
+ *      functor (plugin kind MCIG_PLUGIN_CALLBACK, nvalues ignored) invoked by every walker:
+ *          template <class XO, class XN> __device__ void operator()(const XO & xold, const XN & xnew, bool accepted,
+ *                                                                   long long walker (global id), long long step, double * buffer) const;
+ *      `buffer` has buffer_doubles doubles of device memory owned by the integrator, zeroed at the start of every integrate call and
+ *      readable afterwards with mcig_get_callback_buffer. Walkers run concurrently: index the buffer by walker or use atomicAdd. */
+int mcig_set_callback(mcig_ctx * ctx, int plugin_id, const double * par, int npar, int64_t buffer_doubles);
+int mcig_clear_callback(mcig_ctx * ctx);
+int mcig_get_callback_buffer(mcig_ctx * ctx, double * out, int64_t n);
 
 /* ---- automatic routines: setTargetAcceptanceRate / setNfindMRT2Iterations / setNdecorrelationSteps
  *      include/mci/MCIntegrator.hpp:113-123 (N<0 auto with max |N|, 0 off, N>0 fixed) */

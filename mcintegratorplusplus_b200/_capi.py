@@ -45,6 +45,9 @@ SIGNATURES = {
     "mcig_pop_pdf": (C.c_int, [_ctx]),
     "mcig_clear_pdfs": (C.c_int, [_ctx]),
     "mcig_add_obs": (C.c_int, [_ctx, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mcig_set_callback": (C.c_int, [_ctx, C.c_int, _dp, C.c_int, C.c_int64]),
+    "mcig_clear_callback": (C.c_int, [_ctx]),
+    "mcig_get_callback_buffer": (C.c_int, [_ctx, _dp, C.c_int64]),
     "mcig_pop_obs": (C.c_int, [_ctx]),
     "mcig_clear_obs": (C.c_int, [_ctx]),
     "mcig_get_nobsdim": (C.c_int, [_ctx]),

@@ -82,9 +82,16 @@ class Observable(Plugin):
     kind = 1
 
 
-def register_plugin(kind, name, type_expr, source, ndim=0, nvalues=0, npar=0, has_update=False, elementwise=False, log_acceptance=False):
-    """Register a user functor (CUDA C++ source, see csrc/device/mcig_functors.cuh for the contract)."""
-    flags = (1 if has_update else 0) | (2 if elementwise else 0) | (4 if log_acceptance else 0)
+class StepCallback(Plugin):
+    """MCI::setCallback as a device functor (see include/mcig.h: mcig_set_callback)."""
+    kind = 2
+
+
+def register_plugin(kind, name, type_expr, source, ndim=0, nvalues=0, npar=0, has_update=False, elementwise=False, log_acceptance=False,
+                    dependent=False):
+    """Register a user functor (CUDA C++ source, see csrc/device/mcig_functors.cuh for the contract).
+    kind: 0 sampling function, 1 observable (dependent=True: DependentObservableInterface), 2 step callback."""
+    flags = (1 if has_update else 0) | (2 if elementwise else 0) | (4 if log_acceptance else 0) | (8 if dependent else 0)
     pid = _capi.lib().mcig_register_plugin(kind, name.encode(), type_expr.encode(), (source or "").encode(), ndim, nvalues, npar, flags)
     if pid < 0:
         raise _capi.McigError(-pid, _capi.lib().mcig_last_error().decode())
@@ -248,6 +255,19 @@ class MCI:
             estim = selectEstimatorType(estim, blocksize > 0)
         a, p = _darr(obs.par)
         _capi.check(self._lib.mcig_add_obs(self._ctx, obs.plugin_id(), p, len(obs.par), blocksize, nskip, int(bool(flag_equil)), int(estim)))
+
+    def setCallback(self, callback, buffer_doubles):
+        """setCallback(StepCallback, size of its device buffer in doubles); the buffer is zeroed at every integrate call"""
+        a, p = _darr(callback.par)
+        _capi.check(self._lib.mcig_set_callback(self._ctx, callback.plugin_id(), p, len(callback.par), int(buffer_doubles)))
+        self._cb_doubles = int(buffer_doubles)
+
+    def clearCallback(self): _capi.check(self._lib.mcig_clear_callback(self._ctx))
+
+    def getCallbackBuffer(self):
+        out = np.zeros(self._cb_doubles)
+        _capi.check(self._lib.mcig_get_callback_buffer(self._ctx, out.ctypes.data_as(_dp), self._cb_doubles))
+        return out
 
     def popObservable(self): _capi.check(self._lib.mcig_pop_obs(self._ctx))
     def clearObservables(self): _capi.check(self._lib.mcig_clear_obs(self._ctx))

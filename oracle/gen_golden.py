@@ -57,6 +57,21 @@ def main():
              os.path.join(OUT, "dump_walker.txt").encode(), configs.DUMP_WLK_FREQ) == 0
     print("dump_files", list(res.avg[:res.nobsdim]))
 
+    # step callback (MCI::setCallback) folded into four sums by the harness
+    fcb = ref.lib.mciref_run_callback
+    fcb.restype = C.c_int
+    fcb.argtypes = [C.POINTER(orc.Config), C.POINTER(orc.Result), C.POINTER(C.c_double)]
+    cbs = {}
+    for name in configs.CALLBACK_RUNS:
+        cfg = configs.make(name)
+        res = orc.Result()
+        buf = (C.c_double*4)()
+        assert fcb(C.byref(cfg), C.byref(res), buf) == 0
+        cbs[name] = {"buf": hx(buf), "acc_rate": float(res.acc_rate).hex(), "avg": hx(res.avg[:res.nobsdim])}
+        print("callback", name, list(buf))
+    with open(os.path.join(OUT, "ref_callback.json"), "w") as f:
+        json.dump(cbs, f, indent=1, sort_keys=True)
+
     est = {}
     for wname, (pdf, nmc, ndim, step, cp, seed) in configs.WALKS.items():
         datax, datacc, nchanged, cidx, rate = ref.testwalk(pdf, nmc, ndim, step, cp, seed)

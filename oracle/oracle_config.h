@@ -44,7 +44,8 @@ enum {
     ORC_OBS_X2SUM = 9,        /* X2Sum         :423-442 */
     ORC_OBS_X2 = 10,          /* X2(ndim)      :445-473 (updateable) */
     ORC_OBS_PARABOLA = 11,    /* Parabola           examples/common/ExampleFunctions.hpp:11-29 (1-D 4x-x^2) */
-    ORC_OBS_NORMPARABOLA = 12 /* NormalizedParabola examples/common/ExampleFunctions.hpp:32-50 */
+    ORC_OBS_NORMPARABOLA = 12,/* NormalizedParabola examples/common/ExampleFunctions.hpp:32-50 */
+    ORC_OBS_DEPENDENT = 13    /* reference harness only (oracle/ref_harness.cpp: HarnessDepObs, a DependentObservableInterface): goldens */
 };
 
 /* trial moves: include/mci/Factories.hpp:108-145 */

@@ -13,7 +13,7 @@ MAXDIM, MAXOBS, MAXTYPES, MAXOBSDIM = 1024, 8, 8, 2048
 
 PDF_NONE, PDF_GAUSS3D, PDF_GAUSS, PDF_EXP1D, PDF_EXPND, PDF_NORMLINE = range(6)
 (OBS_XSQUARED, OBS_GAUSSXSQUARED, OBS_XYZSQUARED, OBS_X1D, OBS_XND, OBS_UPDXND, OBS_CONSTVAL, OBS_POLYNOM,
- OBS_X2SUM, OBS_X2, OBS_PARABOLA, OBS_NORMPARABOLA) = range(1, 13)
+ OBS_X2SUM, OBS_X2, OBS_PARABOLA, OBS_NORMPARABOLA, OBS_DEPENDENT) = range(1, 14)
 MOVE_ALL, MOVE_VEC, MOVE_MULTISTEP = range(3)
 SRRD_UNIFORM, SRRD_GAUSSIAN = range(2)
 EST_NOOP, EST_UNCORRELATED, EST_CORRELATED, EST_FCBLOCKER, EST_MJBLOCKER = range(5)
@@ -23,7 +23,7 @@ DOMAIN_UNBOUND, DOMAIN_ORTHO = range(2)
 OBS_NOBS = {  # nobs as a function of ndim
     OBS_XSQUARED: lambda nd: 1, OBS_GAUSSXSQUARED: lambda nd: 1, OBS_XYZSQUARED: lambda nd: 3, OBS_X1D: lambda nd: 1,
     OBS_XND: lambda nd: nd, OBS_UPDXND: lambda nd: nd, OBS_CONSTVAL: lambda nd: 1, OBS_POLYNOM: lambda nd: 1,
-    OBS_X2SUM: lambda nd: 1, OBS_X2: lambda nd: nd, OBS_PARABOLA: lambda nd: 1, OBS_NORMPARABOLA: lambda nd: 1,
+    OBS_X2SUM: lambda nd: 1, OBS_X2: lambda nd: nd, OBS_PARABOLA: lambda nd: 1, OBS_NORMPARABOLA: lambda nd: 1, OBS_DEPENDENT: lambda nd: 2,
 }
 
 

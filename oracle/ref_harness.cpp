@@ -56,6 +56,35 @@ static std::unique_ptr<SamplingFunctionInterface> make_pdf(int id, int ndim)
     }
 }
 
+// A dependent observable (include/mci/DependentObservableInterface.hpp) for the golden vectors of the device-side replacement:
+// depends on the sampling function (sum of the first pdf's proto values at the current position) and on observable 0.
+//   out[0] = sum_i protoold_i + obs0[0]        out[1] = x[0]*obs0[0]
+class HarnessDepObs final: public ObservableFunctionInterface, public DependentObservableInterface
+{
+    const SamplingFunctionInterface * _pdf = nullptr;
+    const AccumulatorInterface * _dep = nullptr;
+
+protected:
+    ObservableFunctionInterface * _clone() const final { return new HarnessDepObs(_ndim); }
+
+public:
+    explicit HarnessDepObs(int ndim): ObservableFunctionInterface(ndim, 2, false), DependentObservableInterface(true) {}
+    void registerDeps(const SamplingFunctionContainer &pdfcont, const std::vector<AccumulatorInterface *> &accuvec, int selfIdx) final
+    {
+        if (selfIdx < 1 || !isObsDepValid(accuvec, selfIdx, 0)) { throw std::runtime_error("HarnessDepObs: invalid dependency"); }
+        _pdf = &pdfcont.getSamplingFunction(0);
+        _dep = accuvec[0];
+    }
+    void deregisterDeps() final { _pdf = nullptr; _dep = nullptr; }
+    void observableFunction(const double in[], double out[]) final
+    {
+        double s = 0.;
+        for (int i = 0; i < _pdf->getNProto(); ++i) { s += _pdf->_protoold[i]; }
+        out[0] = s + _dep->getObsValue(0);
+        out[1] = in[0]*_dep->getObsValue(0);
+    }
+};
+
 static std::unique_ptr<ObservableFunctionInterface> make_obs(int id, int ndim)
 {
     switch (id) {
@@ -71,6 +100,7 @@ static std::unique_ptr<ObservableFunctionInterface> make_obs(int id, int ndim)
     case ORC_OBS_X2: return std::make_unique<X2>(ndim);
     case ORC_OBS_PARABOLA: return std::make_unique<Parabola>();
     case ORC_OBS_NORMPARABOLA: return std::make_unique<NormalizedParabola>();
+    case ORC_OBS_DEPENDENT: return std::make_unique<HarnessDepObs>(ndim);
     default: throw std::invalid_argument("ref_harness: unknown obs id");
     }
 }
@@ -237,6 +267,41 @@ int mciref_run_with_files(const orc_config_t * cfg, orc_result_t * res, const ch
         std::copy(avg.begin(), avg.begin() + nobsdim, res->avg);
         std::copy(err.begin(), err.begin() + nobsdim, res->err);
         res->acc_rate = mci.getAcceptanceRate();
+        return 0;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// integrate() with a step callback (MCI::setCallback, include/mci/MCIntegrator.hpp:186-190) that folds what it sees into four sums:
+// golden values for the device-functor replacement.  buf[0] calls, buf[1] accepted calls, buf[2] sum of the first coordinate of
+// the state the move leads to, buf[3] sum of the proposed displacement of the last coordinate.
+int mciref_run_callback(const orc_config_t * cfg, orc_result_t * res, double * buf)
+{
+    try {
+        const orc_config_t &c = *cfg;
+        MCI mci(c.ndim);
+        configure(mci, c);
+        const int nobsdim = mci.getNObsDim();
+        std::vector<double> avg(std::max(1, nobsdim), 0.), err(std::max(1, nobsdim), 0.);
+        for (int k = 0; k < 4; ++k) { buf[k] = 0.; }
+        const int last = c.ndim - 1;
+        mci.setCallback([&](const MCI &m) {
+            const WalkerState &w = m._wlkstate;
+            buf[0] += 1.;
+            buf[1] += w.accepted ? 1. : 0.;
+            buf[2] += w.accepted ? w.xnew[0] : w.xold[0];
+            buf[3] += w.xnew[last] - w.xold[last];
+        });
+        mci.integrate(c.nmc, avg.data(), err.data(), c.do_find != 0, c.do_decorr != 0);
+        std::memset(res, 0, sizeof(*res));
+        res->nobsdim = nobsdim;
+        std::copy(avg.begin(), avg.begin() + nobsdim, res->avg);
+        std::copy(err.begin(), err.begin() + nobsdim, res->err);
+        res->acc_rate = mci.getAcceptanceRate();
+        for (int i = 0; i < c.ndim; ++i) { res->x_final[i] = mci.getX(i); }
         return 0;
     }
     catch (const std::exception &e) {

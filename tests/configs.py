@@ -70,6 +70,12 @@ RUNS = {
                        x0=_alt(256)),
     "ndim_all1024": dict(ndim=1024, seed=17, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_X2SUM, 4, 1)], nmc=256, steps=(0.03,), x0=_alt(1024)),
     "ndim_vec1024": dict(ndim=1024, seed=18, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 8)], nmc=4096, move_type=orc.MOVE_VEC, veclen=2, steps=(1.0,), x0=_alt(1024)),
+    # --- dependent observables (include/mci/DependentObservableInterface.hpp; reference side: oracle/ref_harness.cpp HarnessDepObs)
+    "dep_obs_all": dict(ndim=3, seed=301, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_DEPENDENT, 4, 2)], nmc=8192, steps=(0.8,)),
+    "dep_obs_vec": dict(ndim=4, seed=302, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 0, 1), (orc.OBS_DEPENDENT, 1, 1), (orc.OBS_XND, 0, 1)], nmc=8192,
+                        move_type=orc.MOVE_VEC, veclen=1, steps=(1.1,)),
+    "dep_obs_auto": dict(ndim=3, seed=303, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1), (orc.OBS_DEPENDENT, 1, 1)], nmc=4096, x0=(1., -1., 2.),
+                         do_find=True, do_decorr=True),
     # --- MultiStepMove
     "ms_default4": dict(ndim=4, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1)], nmc=50000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.7,)),
     "ms_sub_ut5": dict(ndim=3, seed=1337, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_X2, 1, 3)], nmc=32768*3, move_type=orc.MOVE_MULTISTEP,
@@ -128,7 +134,11 @@ DUMP_OBS_FREQ, DUMP_WLK_FREQ = 100, 250
 
 def in_oracle(name):
     """The plain-C oracle restates the uniform and normal proposal distributions; the rest is pinned by the goldens only."""
-    return RUNS[name].get("srrd", 0) < 2
+    return RUNS[name].get("srrd", 0) < 2 and all(tuple(o)[0] != orc.OBS_DEPENDENT for o in RUNS[name]["obs"])
+
+
+# configurations whose step callback sums are pinned by the reference (oracle/ref_harness.cpp: mciref_run_callback)
+CALLBACK_RUNS = ["c1_simple_short", "vec_exp4", "ms_sub16", "auto_default", "ut2_irange", "nopdf_box", "gauss_vec6_v3"]
 
 
 def make(name):

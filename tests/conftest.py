@@ -39,6 +39,11 @@ def golden_runs():
 
 
 @pytest.fixture(scope="session")
+def golden_callback():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "ref_callback.json")))
+
+
+@pytest.fixture(scope="session")
 def golden_est():
     return json.load(open(os.path.join(ROOT, "tests", "golden", "ref_estimators.json")))
 

@@ -16,6 +16,58 @@
 
 using namespace mci;
 
+// A user-defined dependent observable (reference: a class deriving from ObservableFunctionInterface AND
+// DependentObservableInterface): local "energy" = sum of the pdf's proto values, plus a product with observable 0.
+class ProtoSumObs final: public ObservableFunctionInterface, public DependentObservableInterface
+{
+protected:
+    ObservableFunctionInterface * _clone() const final { return new ProtoSumObs(_ndim); }
+
+public:
+    explicit ProtoSumObs(int ndim): ObservableFunctionInterface(ndim, 2, false), DependentObservableInterface(true) {}
+    DeviceFunctor deviceFunctor() const final
+    {
+        return DeviceFunctor("ProtoSumObs", "user::ProtoSumObs<{ndim}>", R"(
+namespace user {
+template <int NDIM> struct ProtoSumObs {
+    const double * par;
+    template <class XV, class DEP> __device__ void observableFunction(const XV & x, double * out, const DEP & dep) const
+    {
+        double s = 0.;
+        for (int i = 0; i < NDIM; ++i) { s += dep.proto(i); }
+        out[0] = s;
+        out[1] = x[0]*x[0] - dep.obs(0, 0)/1.; // observable 0 is X2Sum: x0^2 - sum x^2
+    }
+};
+})");
+    }
+};
+
+// A user-defined step callback: per-walker count of calls and of accepted moves
+class CountingCallback final: public StepCallbackInterface
+{
+protected:
+    StepCallbackInterface * _clone() const final { return new CountingCallback(); }
+
+public:
+    int64_t bufferDoubles(int64_t nwalkers) const final { return 2*nwalkers; }
+    DeviceFunctor deviceFunctor() const final
+    {
+        return DeviceFunctor("CountingCallback", "user::CountingCallback", R"(
+namespace user {
+struct CountingCallback {
+    const double * par;
+    template <class XO, class XN> __device__ void operator()(const XO &, const XN &, bool accepted, long long walker, long long step, double * buf) const
+    {
+        if (step < 0) { return; } // the call from initializeSampling
+        buf[2*walker] += 1.;
+        buf[2*walker + 1] += accepted ? 1. : 0.;
+    }
+};
+})");
+    }
+};
+
 template <class E, class F>
 static bool throws(F f)
 {
@@ -145,6 +197,29 @@ static void test_gpu()
         assert(fabs(avg[0] - 0.49129926481208264) < 1e-12*0.5);
         assert(mci.getAcceptanceRate() == 0.50334);
         assert(mci.getX(0) == 0.56622698245761904 && mci.getX(2) == 0.65777044965711584);
+    }
+    { // dependent observable + step callback as device functors
+        MCI mci(3);
+        mci.setSeed(99);
+        mci.setNWalkers(512);
+        mci.setMRT2Step(0.9);
+        mci.addSamplingFunction(Gauss(3));
+        mci.addObservable(X2Sum(3), 1, 1);
+        mci.addObservable(ProtoSumObs(3), 1, 1);
+        mci.setCallback(CountingCallback());
+        assert(throws<std::logic_error>([&] { mci.setCallback([](const MCI &) {}); }));
+        double a[3], e[3];
+        mci.integrate(4096, a, e, false, false);
+        assert(fabs(a[0] - 1.5) < 4.*e[0]);             // <sum x^2> = 3 * 0.5
+        assert(fabs(a[1] - a[0]) < 1e-12);               // Gauss proto values are x_i^2: their sum is X2Sum, sample by sample
+        assert(fabs(a[2] + 1.0) < 4.*e[2]);              // <x0^2 - sum x^2> = -1
+        const std::vector<double> buf = mci.getCallbackBuffer();
+        assert(buf.size() == 1024);
+        double calls = 0., acc = 0.;
+        for (size_t w = 0; w < 512; ++w) { calls += buf[2*w]; acc += buf[2*w + 1]; }
+        assert(calls == 512.*4096. && fabs(acc/calls - mci.getAcceptanceRate()) < 1e-12);
+        mci.clearCallback();
+        mci.integrate(4096, a, e, false, false);
     }
     { // free estimator functions on host data
         std::vector<double> x(4096);

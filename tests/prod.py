@@ -5,12 +5,57 @@ PDF_NAMES = {orc.PDF_GAUSS3D: "ThreeDimGaussianPDF", orc.PDF_GAUSS: "Gauss", orc
              orc.PDF_NORMLINE: "NormalizedLine"}
 OBS_NAMES = {orc.OBS_XSQUARED: "XSquared", orc.OBS_GAUSSXSQUARED: "GaussXSquared", orc.OBS_XYZSQUARED: "XYZSquared", orc.OBS_X1D: "X1D",
              orc.OBS_XND: "XND", orc.OBS_UPDXND: "UpdateableXND", orc.OBS_CONSTVAL: "Constval", orc.OBS_POLYNOM: "Polynom",
-             orc.OBS_X2SUM: "X2Sum", orc.OBS_X2: "X2", orc.OBS_PARABOLA: "Parabola", orc.OBS_NORMPARABOLA: "NormalizedParabola"}
+             orc.OBS_X2SUM: "X2Sum", orc.OBS_X2: "X2", orc.OBS_PARABOLA: "Parabola", orc.OBS_NORMPARABOLA: "NormalizedParabola",
+             orc.OBS_DEPENDENT: "HarnessDepObs"}
+
+# Device twins of the reference-side test classes in oracle/ref_harness.cpp (user plugins: CUDA C++ source compiled by NVRTC)
+DEP_OBS_SRC = """
+namespace test_plugins {
+template <int NDIM>
+struct HarnessDepObs { // DependentObservableInterface: sum of the pdf's proto values + observable 0, and x[0]*observable 0
+    const double * par;
+    template <class XV, class DEP>
+    __device__ void observableFunction(const XV & in, double * out, const DEP & dep) const
+    {
+        double s = 0.;
+        for (int i = 0; i < NDIM; ++i) { s += dep.proto(i); } // Gauss(ndim): one proto value per coordinate
+        out[0] = s + dep.obs(0, 0);
+        out[1] = in[0]*dep.obs(0, 0);
+    }
+};
+}
+"""
+CALLBACK_SRC = """
+namespace test_plugins {
+template <int NDIM>
+struct FoldCallback { // the four sums of mciref_run_callback, one set per walker
+    const double * par;
+    template <class XO, class XN>
+    __device__ void operator()(const XO & xold, const XN & xnew, bool accepted, long long walker, long long step, double * buf) const
+    {
+        double * b = buf + 6*walker;
+        b[0] += 1.;
+        b[1] += accepted ? 1. : 0.;
+        b[2] += accepted ? xnew[0] : xold[0];
+        b[3] += xnew[NDIM - 1] - xold[NDIM - 1];
+        b[4] += (double)step;
+        b[5] = (double)step;
+    }
+};
+}
+"""
+
+
+def register_test_plugins(m):
+    m.register_plugin(1, "HarnessDepObs", "test_plugins::HarnessDepObs<{ndim}>", DEP_OBS_SRC, ndim=0, nvalues=2, npar=0, dependent=True)
+    m.register_plugin(2, "FoldCallback", "test_plugins::FoldCallback<{ndim}>", CALLBACK_SRC, ndim=0, npar=0)
+
 
 
 def build_mci(m, spec, nwalkers=1, mode=None, seeds=None, placement=None):
     kw = dict(spec)
     ndim = kw["ndim"]
+    register_test_plugins(m)
     mci = m.MCI(ndim)
     mci.setRngMode(m.RngMode.Replay if mode is None else mode)
     if nwalkers != 1:

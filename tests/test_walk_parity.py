@@ -275,3 +275,44 @@ def test_thousand_dimensional_walkers_sample_the_right_distribution(mcig):
     # 2048 walkers x 40 sweeps of correlated samples per coordinate: standard error ~ 0.5*sqrt(2)/sqrt(2048*40/4) ~ 0.005
     assert avg.shape == (nd,) and np.all(np.abs(avg - 0.5) < 0.03), (avg.min(), avg.max())
     assert abs(avg.mean() - 0.5) < 2e-3
+
+
+@pytest.mark.parametrize("name", configs.CALLBACK_RUNS)
+def test_step_callback_matches_reference(name, mcig, golden_callback):
+    """MCI::setCallback as a device functor: called once at the start of every sampling run and after every move (calibration and
+    decorrelation runs included), with the pre-commit state. The four sums the reference-side harness callback folds must agree."""
+    spec = configs.RUNS[name]
+    g = golden_callback[name]
+    mci = build_mci(mcig, spec)
+    mci.setCallback(mcig.StepCallback("FoldCallback"), 6)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    buf = mci.getCallbackBuffer()
+    ref = fromhex(g["buf"])
+    assert buf[0] == ref[0] and buf[1] == ref[1], (buf, ref)
+    assert _close(buf[2:4], ref[2:4], 1e-12, atol=1e-12), (buf, ref)
+    assert mci.getAcceptanceRate() == float.fromhex(g["acc_rate"])
+    assert buf[5] == spec["nmc"] - 1  # the last call saw the last step of the main run
+    if not spec.get("do_find", False) and not spec.get("do_decorr", False):
+        n = spec["nmc"]
+        assert buf[4] == n*(n - 1)/2 - 1  # steps -1 (initializeSampling), 0 .. n-1
+    mci.clearCallback()
+    avg2, _ = mci.integrate(spec["nmc"], False, False)
+    assert avg2.shape == avg.shape
+
+
+def test_step_callback_many_walkers_philox(mcig):
+    nd, W, n = 3, 4096, 1000
+    mci = mcig.MCI(nd)
+    mci.setRngMode(0)
+    mci.setNWalkers(W)
+    mci.setSeed(5)
+    mci.addSamplingFunction(mcig.ThreeDimGaussianPDF())
+    mci.addObservable(mcig.XSquared(), 0, 1)
+    mci.setMRT2Step(1.0)
+    from prod import register_test_plugins
+    register_test_plugins(mcig)
+    mci.setCallback(mcig.StepCallback("FoldCallback"), 6*W)
+    mci.integrate(n, False, False)
+    buf = mci.getCallbackBuffer().reshape(W, 6)
+    assert np.all(buf[:, 0] == n + 1) and np.all(buf[:, 5] == n - 1)
+    assert buf[:, 1].sum() - W == round(mci.getAcceptanceRate()*W*n)  # per-walker accept counts add up to the global rate
