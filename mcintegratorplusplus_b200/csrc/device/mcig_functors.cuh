@@ -24,8 +24,22 @@
 //       const double * par;
 //       template <class X, class O> __device__ void observableFunction(const X & in, O & out) const;
 //   };
+//   struct MyDependentObs {                         // mirrors a class deriving from mci::DependentObservableInterface as well
+//       const double * par;                         // (registration flag MCIG_PLUGIN_DEPENDENT)
+//       // dep.proto(i): i-th proto value of the sampling functions at the current position (flat over the pdfs in the order added)
+//       // dep.obs(k, j): j-th value of observable k (k < own index, its nskip divides this one's) as evaluated in this step
+//       template <class X, class DEP> __device__ void observableFunction(const X & in, double * out, const DEP & dep) const;
+//   };
+//   struct MyCallback {                             // MCI::setCallback (plugin kind MCIG_PLUGIN_CALLBACK)
+//       const double * par;
+//       // called by every walker after each accept decision, before the commit (xold, xnew as the reference's WalkerState holds
+//       // them at src/MCIntegrator.cpp:346), and once per sampling run with step = -1 (initializeSampling, :267);
+//       // buffer: the integrator-owned device buffer of mcig_set_callback, shared by all walkers (index by walker or atomicAdd)
+//       template <class XO, class XN> __device__ void operator()(const XO & xold, const XN & xnew, bool accepted, long long walker,
+//                                                                long long step, double * buffer) const;
+//   };
 //
-// X / P / O are array-like (double* or a strided shared-memory view): index them with [], nothing else.
+// X / P / O are array-like (double*, a strided shared- or global-memory view): index them with [], nothing else.
 // ndim / nproto / nobs are declared to the host through the C-ABI registration (include/mcig.h).
 //
 // Arithmetic note: expressions keep the reference's operation order so that the replay mode (compiled with
