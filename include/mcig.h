@@ -170,6 +170,10 @@ int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double 
 /* ---- engine knobs without reference analogue */
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
 int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory, 2 global memory (auto picks 2 when a warp of walkers exceeds 227 KiB) */
+/* Element-wise observables (plugin flag MCIG_PLUGIN_ELEMENTWISE, e.g. XND, X2) in Simple / Block accumulators under single-vector
+ * moves: add value x dwell time when a coordinate changes instead of every component at every step. 1 (default): in the Philox
+ * modes, replay mode keeps the reference's summation order; 2: in every mode; 0: never. Sums differ by rounding only. */
+int mcig_set_lazy_accumulation(mcig_ctx * ctx, int on);
 /* findMRT2Step feedback loop on the device (default 1: sampling launch -> acceptance reduction -> controller kernel, no host
  * synchronisation per iteration; used in the Philox modes of a single-process job) or on the host (0: one 8-byte readback per
  * iteration; always used in replay mode and when a cross-process sum is installed). Same arithmetic, same results. */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mcig_set_state_placement": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_dynamic_scheduling": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_philox_rounds": (C.c_int, [_ctx, C.c_int]),
+    "mcig_set_lazy_accumulation": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_device_calibration": (C.c_int, [_ctx, C.c_int]),
     "mcig_get_calibration_iterations": (C.c_int, [_ctx]),
     "mcig_store_on_file": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int]),

@@ -23,6 +23,10 @@
 //       static constexpr int NPAR = 0;
 //       const double * par;
 //       template <class X, class O> __device__ void observableFunction(const X & in, O & out) const;
+//       // optional (registration flag MCIG_PLUGIN_ELEMENTWISE, nobs == ndim): out[j] as a function of in[j] alone. Under single-vector
+//       // moves Simple / Block accumulators then add value x dwell time when a coordinate changes instead of every component at
+//       // every step (the device counterpart of updatedObservable + flags_xchanged, src/AccumulatorInterface.cpp:55-85)
+//       __device__ double observableElement(double xj) const;
 //   };
 //   struct MyDependentObs {                         // mirrors a class deriving from mci::DependentObservableInterface as well
 //       const double * par;                         // (registration flag MCIG_PLUGIN_DEPENDENT)
@@ -283,6 +287,7 @@ struct XND { // TestMCIFunctions.hpp:339-379 (XND and UpdateableXND compute the 
 #pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { out[i] = in[i]; }
     }
+    MCIG_DEV double observableElement(double xj) const { return xj; } // element-wise: out[j] is a function of in[j] alone
 };
 
 struct Constval { // TestMCIFunctions.hpp:382-398
@@ -330,6 +335,7 @@ struct X2 { // TestMCIFunctions.hpp:445-473
 #pragma unroll MCIG_UNROLL_N(NDIM)
         for (int i = 0; i < NDIM; ++i) { out[i] = in[i]*in[i]; }
     }
+    MCIG_DEV double observableElement(double xj) const { return xj*xj; }
 };
 
 struct Parabola { // ExampleFunctions.hpp:11-29

@@ -215,3 +215,22 @@ def test_device_resident_calibration_equals_host_loop(name, mcig):
         out.append(([mci.getMRT2Step(i) for i in range(nt)], mci.getCalibrationIterations(), avg.copy(), err.copy(), mci.getAcceptanceRate()))
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1] and out[0][1] >= 1
     assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3]) and out[0][4] == out[1][4]
+
+
+@pytest.mark.parametrize("name", ["vec_exp4", "ndim_vec16", "ndim_vec64_v4", "vec_ortho_types", "ndim_vec300_v3_types"])
+def test_lazy_accumulation_equals_per_step_accumulation(name, mcig):
+    """Element-wise observables under single-vector moves are accumulated as value x dwell time; the trajectories are untouched
+    (same acceptance, same final positions) and the sums agree with the per-step additions to rounding."""
+    spec = dict(configs.RUNS[name])
+    spec["obs"] = [(orc.OBS_XND, 0, 1), (orc.OBS_X2, 16, 1), (orc.OBS_X2SUM, 1, 1)]
+    out = []
+    for lazy in (1, 0):
+        mci = build_mci(mcig, spec, nwalkers=64, mode=0)
+        mci.setLazyAccumulation(lazy)
+        avg, err = mci.integrate(4096, False, False)
+        out.append((avg.copy(), err.copy(), mci.getAcceptanceRate(), list(mci.getX()), "LazyAccu" in mci.kernelSource()))
+    assert out[0][4] and not out[1][4]
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
+    # zero-mean components: the sums of |x| ~ 1 values differ by rounding only, i.e. by ~1e-16 relative to the typical magnitude
+    assert np.max(np.abs(out[0][0] - out[1][0])) < 1e-13, np.max(np.abs(out[0][0] - out[1][0]))
+    assert np.allclose(out[0][1], out[1][1], rtol=1e-9, atol=1e-16)

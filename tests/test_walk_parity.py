@@ -316,3 +316,20 @@ def test_step_callback_many_walkers_philox(mcig):
     buf = mci.getCallbackBuffer().reshape(W, 6)
     assert np.all(buf[:, 0] == n + 1) and np.all(buf[:, 5] == n - 1)
     assert buf[:, 1].sum() - W == round(mci.getAcceptanceRate()*W*n)  # per-walker accept counts add up to the global rate
+
+
+@pytest.mark.parametrize("name", ["vec_exp4", "ndim_vec16", "ndim_vec64_v4", "ndim_vec300_v3_types"])
+def test_lazy_accumulation_against_the_reference(name, mcig, golden_runs):
+    """Value x dwell-time accumulation forced on in replay mode: same trajectory as the reference (bit-exact), sums equal to the
+    reference's step-by-step additions up to the rounding of the summation order (1e-12 of the observable's scale)."""
+    spec = configs.RUNS[name]
+    g = golden_runs[name]
+    mci = build_mci(mcig, spec)
+    mci.setLazyAccumulation(2)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    assert "LazyAccu" in mci.kernelSource()
+    assert mci.getAcceptanceRate() == float.fromhex(g["acc_rate"]) and list(mci.getX()) == fromhex(g["x_final"])
+    ref = np.array(fromhex(g["avg"]))
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    assert np.max(np.abs(avg - ref)) <= 1e-12*scale, np.max(np.abs(avg - ref))
+    assert _close(err, fromhex(g["err"]), 1e-9, atol=1e-15)

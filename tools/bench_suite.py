@@ -104,6 +104,9 @@ if __name__ == "__main__":
         c3_ndim("vec")
         c3_ndim("all")
         c3_ndim("multistep", ndims=(2, 4, 8, 16, 32))
+    if "c3vec" in which:
+        c3_ndim("vec")
+        c3_ndim("vec", ndims=(128, 256, 512, 1024), W=65536, nmc=4000)
     if "c3big" in which:  # the upper half of the reference's dimension sweeps (benchmark/bench_throughput_ndim_*: up to 1024)
         c3_ndim("vec", ndims=(128, 256, 512, 1024), W=16384, nmc=20000)
         c3_ndim("all", ndims=(128, 256, 512, 1024), W=16384, nmc=2000)
