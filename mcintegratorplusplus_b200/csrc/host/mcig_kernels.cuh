@@ -381,69 +381,6 @@ __device__ __forceinline__ double fc_err_delta(int mode, const double * e /*cent
     }
 }
 
-__global__ void fcblocker_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, double * __restrict__ wavg,
-                                 double * __restrict__ werr)
-{
-    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
-    if (col >= ncol) { return; }
-    constexpr int MINB = 6, MAXB = 50, NAV = MAXB - MINB + 1, MPA = 4, NACCD = NAV - 2*MPA;
-    double bsum[NAV], s1[NAV], s2[NAV];
-    int left[NAV];   // samples left in the current block
-    int bdone[NAV];  // completed blocks
-    for (int a = 0; a < NAV; ++a) {
-        bsum[a] = 0.; s1[a] = 0.; s2[a] = 0.;
-        left[a] = (int)(n/(a + MINB));
-        bdone[a] = 0;
-    }
-    for (i64 i = 0; i < n; ++i) {
-        const double v = __ldcs(data + i*ncol + col);
-        for (int a = 0; a < NAV; ++a) {
-            if (bdone[a] == a + MINB) { continue; } // remainder samples are ignored (Estimators.cpp:65, :164)
-            bsum[a] = __dadd_rn(bsum[a], v);
-            if (--left[a] == 0) {
-                const i64 nper = n/(a + MINB);
-                const double av = __dmul_rn(bsum[a], 1./(double)nper);
-                s1[a] = __dadd_rn(s1[a], av);
-                s2[a] = __dadd_rn(s2[a], __dmul_rn(av, av));
-                bsum[a] = 0.;
-                left[a] = (int)nper;
-                ++bdone[a];
-            }
-        }
-    }
-    double av[NAV], err[NAV];
-    for (int a = 0; a < NAV; ++a) {
-        const double nb = (double)(a + MINB);
-        const double norm = 1./nb;
-        const double mean = __dmul_rn(s1[a], norm);
-        double er = __dadd_rn(__dmul_rn(s2[a], norm), -__dmul_rn(mean, mean));
-        if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/(nb - 1.)) : sqrt(__dmul_rn(er, 1./(nb - 1.))); }
-        else { er = 0.; }
-        av[a] = mean;
-        err[a] = er;
-    }
-    double accd[NACCD];
-    for (int i2 = MPA; i2 < NACCD + MPA; ++i2) {
-        double acc = 0.;
-        for (int i1 = 1; i1 <= MPA; ++i1) { acc = __dadd_rn(acc, fc_err_delta(i1, err + i2)); }
-        accd[i2 - MPA] = acc;
-    }
-    int imin = 0;
-    for (int i2 = 1; i2 < NACCD; ++i2) {
-        if (fabs(accd[i2]) < fabs(accd[imin])) { imin = i2; }
-    }
-    imin += MPA;
-    wavg[col] = 0.2*(av[imin - 2] + av[imin - 1] + av[imin] + av[imin + 1] + av[imin + 2]);
-    werr[col] = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
-}
-
-
-// Event-driven FCBlocker for long series: ONE streaming pass with a single running sum per chain. The (position, partition)
-// pairs at which some partition completes a block are precomputed on the host and sorted by position (<= 1260 events);
-// a block sum is the difference of the running sum at its two borders. Per sample the thread does one add and one compare,
-// so the kernel streams at HBM speed; the 45 partitions' state (3 doubles each) is touched only at events.
-// Block sums obtained as prefix differences differ from the reference's direct sums by O(1e-16 * |prefix|/|block sum|)
-// relative — far inside the 1e-9 estimator tolerance; series up to MCIG_FC_EXACT_MAX samples use the exact kernel above.
 #define MCIG_FC_EXACT_MAX 4096
 __device__ __forceinline__ double fc_tree16(const double * v)
 { // pairwise sum: dependency depth 4 instead of 16 (the running sum is a latency chain: one thread per chain, few warps per SM)
@@ -508,6 +445,81 @@ __device__ __forceinline__ void fc_finish(const double * s1, const double * s2, 
     out_err = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
 }
 
+// One pass per partition, as the reference does (45 passes, src/Estimators.cpp:207-213), with scalar state. A single pass feeding
+// all 45 partitions needs dynamically indexed per-partition state in local memory (measured 5x slower). Every block sum is
+// accumulated left to right from zero (the reference's order, bit for bit); four blocks of a partition are summed side by side
+// (independent chains: the adds of one chain are 4500 deep per thread) and pushed into the partition's sums in block order.
+template <class LD>
+__device__ __forceinline__ void fc_exact_passes(i64 n, LD ld, double * s1, double * s2)
+{
+    constexpr int MINB = 6, NAV = 45;
+    for (int a = 0; a < NAV; ++a) {
+        const int nb = a + MINB;
+        const i64 nper = n/nb;
+        const double rnper = 1./(double)nper;
+        double t1 = 0., t2 = 0.;
+        int j = 0;
+        for (; j + 4 <= nb; j += 4) {
+            double b0 = 0., b1 = 0., b2 = 0., b3 = 0.;
+            const i64 o0 = (i64)j*nper, o1 = o0 + nper, o2 = o1 + nper, o3 = o2 + nper;
+#pragma unroll 2
+            for (i64 i = 0; i < nper; ++i) {
+                b0 = __dadd_rn(b0, ld(o0 + i));
+                b1 = __dadd_rn(b1, ld(o1 + i));
+                b2 = __dadd_rn(b2, ld(o2 + i));
+                b3 = __dadd_rn(b3, ld(o3 + i));
+            }
+            const double a0 = __dmul_rn(b0, rnper), a1 = __dmul_rn(b1, rnper), a2 = __dmul_rn(b2, rnper), a3 = __dmul_rn(b3, rnper);
+            t1 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(t1, a0), a1), a2), a3);
+            t2 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(t2, __dmul_rn(a0, a0)), __dmul_rn(a1, a1)), __dmul_rn(a2, a2)), __dmul_rn(a3, a3));
+        }
+        for (; j < nb; ++j) {
+            double bsum = 0.;
+            const i64 o = (i64)j*nper;
+            for (i64 i = 0; i < nper; ++i) { bsum = __dadd_rn(bsum, ld(o + i)); }
+            const double av = __dmul_rn(bsum, rnper);
+            t1 = __dadd_rn(t1, av);
+            t2 = __dadd_rn(t2, __dmul_rn(av, av));
+        }
+        s1[a] = t1;
+        s2[a] = t2;
+    }
+}
+
+// series read from global memory 45 times (L2-resident for the sizes this serves: n <= 4096)
+__global__ void fcblocker_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, double * __restrict__ wavg,
+                                 double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    double s1[45], s2[45];
+    const double * src = data + col;
+    fc_exact_passes(n, [&](i64 i) { return __ldg(src + i*ncol); }, s1, s2);
+    fc_finish(s1, s2, nobs_is_one, wavg[col], werr[col]);
+}
+
+// short series (the 100-sample chunks of the decorrelation loop): one warp stages its 32 chains in shared memory [n][32] once
+__global__ void __launch_bounds__(32) fcblocker_smem_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, double * __restrict__ wavg,
+                                                            double * __restrict__ werr)
+{
+    extern __shared__ double fc_tile[];
+    const i64 col = (i64)blockIdx.x*32 + threadIdx.x;
+    const bool live = col < ncol;
+    for (i64 i = 0; i < n; ++i) { fc_tile[i*32 + threadIdx.x] = live ? __ldcs(data + i*ncol + col) : 0.; }
+    if (!live) { return; } // no block-level synchronisation: every thread reads only what it wrote
+    double s1[45], s2[45];
+    const double * src = fc_tile + threadIdx.x;
+    fc_exact_passes(n, [&](i64 i) { return src[i*32]; }, s1, s2);
+    fc_finish(s1, s2, nobs_is_one, wavg[col], werr[col]);
+}
+
+
+// Event-driven FCBlocker for long series: ONE streaming pass with a single running sum per chain. The (position, partition)
+// pairs at which some partition completes a block are precomputed on the host and sorted by position (<= 1260 events);
+// a block sum is the difference of the running sum at its two borders. Per sample the thread does one add and one compare,
+// so the kernel streams at HBM speed; the 45 partitions' state (3 doubles each) is touched only at events.
+// Block sums obtained as prefix differences differ from the reference's direct sums by O(1e-16 * |prefix|/|block sum|)
+// relative — far inside the 1e-9 estimator tolerance; series up to MCIG_FC_EXACT_MAX samples use the exact kernel above.
 // Few long chains (ncol threads would leave the GPU empty): split every chain into nseg time segments. Pass 1 streams segment
 // (seg, col) and records the LOCAL running sum at every block border inside it plus the segment total; pass 2 walks the <= 1260
 // events of a chain in order with global prefix = (sum of earlier segment totals) + local prefix.
