@@ -81,14 +81,14 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     template <class X, class P>
     MCIG_DEV void protoFunction(const X & in, P & pv) const
     {
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { pv[i] = in[i]*in[i]; }
     }
     template <class P>
     MCIG_DEV double samplingFunction(const P & pv) const
     {
         double s = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += pv[i]; }
         return exp(-s);
     }
@@ -96,9 +96,9 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return exp(a - b);
     }
@@ -106,9 +106,9 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return a - b;
     }
@@ -164,14 +164,14 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     template <class X, class P>
     MCIG_DEV void protoFunction(const X & in, P & pv) const
     {
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { pv[i] = fabs(in[i]); }
     }
     template <class P>
     MCIG_DEV double samplingFunction(const P & pv) const
     {
         double s = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += pv[i]; }
         return exp(-s);
     }
@@ -179,9 +179,9 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     MCIG_DEV double acceptanceFunction(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return exp(a - b);
     }
@@ -189,9 +189,9 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     MCIG_DEV double logAcceptance(const PO & po, const PN & pn) const
     {
         double a = 0., b = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { a += po[i]; }
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { b += pn[i]; }
         return a - b;
     }
@@ -284,7 +284,7 @@ struct XND { // TestMCIFunctions.hpp:339-379 (XND and UpdateableXND compute the 
     template <class X, class O>
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { out[i] = in[i]; }
     }
     MCIG_DEV double observableElement(double xj) const { return xj; } // element-wise: out[j] is a function of in[j] alone
@@ -305,7 +305,7 @@ struct Polynom { // TestMCIFunctions.hpp:401-420
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
         double s = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += in[i]; }
         out[0] = s;
     }
@@ -319,7 +319,7 @@ struct X2Sum { // TestMCIFunctions.hpp:423-442
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
         double s = 0.;
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { s += in[i]*in[i]; }
         out[0] = s;
     }
@@ -332,7 +332,7 @@ struct X2 { // TestMCIFunctions.hpp:445-473
     template <class X, class O>
     MCIG_DEV void observableFunction(const X & in, O & out) const
     {
-#pragma unroll MCIG_UNROLL_N(NDIM)
+#pragma unroll mcig::unroll_n(NDIM)
         for (int i = 0; i < NDIM; ++i) { out[i] = in[i]*in[i]; }
     }
     MCIG_DEV double observableElement(double xj) const { return xj*xj; }
