@@ -247,6 +247,24 @@ def main():
     e2e_ms = maxreduce(1e3*(time.perf_counter() - t0))
     e2e_value = samples/(e2e_ms*1e-3)
 
+    # ---- context for the roofline fraction (N = 1 only, outside every timed region): the named workload's 65536 walkers are 3.46 warps
+    # per scheduler on 148 SMs; the same kernel with every scheduler holding 8 warps shows what the instruction stream itself allows
+    full = None
+    if world == 1:
+        wfull = 148*2048
+        mf = m.MCI(3, device=local)
+        mf.setRngMode(m.RngMode.Philox32)
+        mf.setSeed(1337)
+        mf.setNWalkers(wfull)
+        mf.addSamplingFunction(m.ThreeDimGaussianPDF())
+        mf.addObservable(m.XSquared(), 0, 1)
+        mf.setMRT2Step(1.0)
+        mf.setBlockSize(256)
+        for _ in range(2):
+            mf.integrate(NMC, False, False)
+        full = (wfull, float(wfull)*NMC/(mf.timings()["walk_ms"]*1e-3))
+        del mf
+
     if rank == 0:
         steps_per_s_kernel = float(WALKERS_PER_GPU)*NMC*args.steps/(walk_ms_max*1e-3)  # per GPU
         achieved = FP64_INSTR_PER_STEP*steps_per_s_kernel
@@ -264,15 +282,18 @@ def main():
                          "fp64_instr_per_metropolis_step": FP64_INSTR_PER_STEP, "flop_per_metropolis_step": FLOP_PER_STEP,
                          "achieved_tflops": FLOP_PER_STEP*steps_per_s_kernel/1e12, "peak_tflops": 2*peaks[0]/1e12,
                          "peak_source": "DFMA/s measured live by mcig_measure_peaks on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
-                         "imad_peak_ginst": peaks[1]/1e9},
+                         "imad_peak_ginst": peaks[1]/1e9,
+                         "full_occupancy": None if full is None else {
+                             "walkers": full[0], "steps_per_s": full[1], "frac": FP64_INSTR_PER_STEP*full[1]/peaks[0],
+                             "note": "same kernel, 8 warps per scheduler instead of the workload's 3.46; context only, not the bench value"}},
             "clocks": clocks,
             "result": {"avg": float(avg[0]), "err": float(err[0]), "acceptance": float(rate), "cross_walker_err_local": float(mci.crossWalkerError()[0])},
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             nproc = os.cpu_count() or 1
-            v, kind, wall = cpu_reference_run(6000000, nproc)
+            v, kind, wall = cpu_reference_run(15000000, nproc)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": nproc, "kind": kind,
-                                    "sample": "%d independent chains (one per host core) x 6e6 Metropolis steps of the same integrand, %.1f s wall" % (nproc, wall)}
+                                    "sample": "%d independent chains (one per host core) x 1.5e7 Metropolis steps of the same integrand, %.1f s wall" % (nproc, wall)}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
