@@ -81,6 +81,11 @@ int mcig_set_device(mcig_ctx * ctx, int device);
  *      unless per-walker seeds are given (MPIMCI::setSeed, src/MPIMCI.cpp:38-65: rank r <- seed file entry offset+r). */
 int mcig_set_seed(mcig_ctx * ctx, uint64_t seed);
 int mcig_set_walker_seeds(mcig_ctx * ctx, const uint64_t * seeds, int64_t n);
+/* Philox modes: position of every walker's stream, in draw groups (one group = the uniforms of one proposal + its accept test; the
+ * counter-based generator is random-access). integrate advances it; mcig_set_seed resets it to 0. Checkpoint / resume: save the
+ * positions (mcig_get_x), the step sizes and this counter. */
+int mcig_set_stream_position(mcig_ctx * ctx, uint64_t group);
+uint64_t mcig_get_stream_position(mcig_ctx * ctx);
 int mcig_set_rng_mode(mcig_ctx * ctx, int mode);
 
 /* ---- walkers: one reference MCI = one chain; many chains exist there only as MPI ranks (src/MPIMCI.cpp:83).

@@ -27,6 +27,8 @@ SIGNATURES = {
     "mcig_set_device": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_seed": (C.c_int, [_ctx, C.c_uint64]),
     "mcig_set_walker_seeds": (C.c_int, [_ctx, _u64p, C.c_int64]),
+    "mcig_set_stream_position": (C.c_int, [_ctx, C.c_uint64]),
+    "mcig_get_stream_position": (C.c_uint64, [_ctx]),
     "mcig_set_rng_mode": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_walkers": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_int64]),
     "mcig_get_walkers": (C.c_int64, [_ctx]),

@@ -344,6 +344,8 @@ class MCI:
     def storeWalkerPositionsOnFile(self, path, freq): _capi.check(self._lib.mcig_store_on_file(self._ctx, 1, path.encode(), int(freq)))
     def clearObservableFile(self): _capi.check(self._lib.mcig_store_on_file(self._ctx, 0, b"", 0))
     def clearWalkerFile(self): _capi.check(self._lib.mcig_store_on_file(self._ctx, 1, b"", 0))
+    def setStreamPosition(self, group): _capi.check(self._lib.mcig_set_stream_position(self._ctx, int(group)))
+    def getStreamPosition(self): return int(self._lib.mcig_get_stream_position(self._ctx))
     def setLazyAccumulation(self, on): _capi.check(self._lib.mcig_set_lazy_accumulation(self._ctx, int(on)))
     def setDeviceCalibration(self, on): _capi.check(self._lib.mcig_set_device_calibration(self._ctx, int(on)))
     def getCalibrationIterations(self): return self._lib.mcig_get_calibration_iterations(self._ctx)

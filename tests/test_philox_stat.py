@@ -234,3 +234,25 @@ def test_lazy_accumulation_equals_per_step_accumulation(name, mcig):
     # zero-mean components: the sums of |x| ~ 1 values differ by rounding only, i.e. by ~1e-16 relative to the typical magnitude
     assert np.max(np.abs(out[0][0] - out[1][0])) < 1e-13, np.max(np.abs(out[0][0] - out[1][0]))
     assert np.allclose(out[0][1], out[1][1], rtol=1e-9, atol=1e-16)
+
+
+@pytest.mark.parametrize("name", ["c1_simple_short", "vec_exp4", "nopdf_box", "mixed"])
+def test_stream_position_is_resumable_across_a_2_32_boundary(name, mcig):
+    """The Philox group counter is 64 bit and random-access: started 1000 groups before a 2^32 boundary, one run of 2n steps equals two
+    runs of n steps, on the register and on the shared-memory walkers alike, and the stream position advances by the groups consumed."""
+    spec = dict(configs.RUNS[name])
+    n = 4000
+    start = 3*2**32 - 1000
+    out = []
+    for placement, pieces in ((0, 1), (0, 2), (1, 1)):
+        if placement == 1 and spec["pdf_id"] == orc.PDF_NONE:
+            continue
+        mci = build_mci(mcig, spec, nwalkers=96, mode=0, placement=placement)
+        mci.setStreamPosition(start)
+        for _ in range(pieces):
+            mci.integrate(n//pieces, False, False)
+        groups_per_step = 1
+        assert mci.getStreamPosition() == start + n*groups_per_step
+        out.append((mci.getAcceptanceRate() if pieces == 1 else None, list(mci.getX())))
+    assert all(o[1] == out[0][1] for o in out)
+    assert out[-1][0] == out[0][0] or len(out) == 2
