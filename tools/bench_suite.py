@@ -104,6 +104,10 @@ if __name__ == "__main__":
         c3_ndim("vec")
         c3_ndim("all")
         c3_ndim("multistep", ndims=(2, 4, 8, 16, 32))
+    if "c3all" in which:
+        c3_ndim("all")
+        c3_ndim("all", ndims=(128, 256, 1024), W=65536, nmc=1000)
+        c3_ndim("multistep", ndims=(2, 4, 8, 16, 32, 64))
     if "c3vec" in which:
         c3_ndim("vec")
         c3_ndim("vec", ndims=(128, 256, 512, 1024), W=65536, nmc=4000)
