@@ -18,6 +18,8 @@ inline void MJBlockerEstimator(int64_t n, int ndim, const double x[], double ave
 inline void MultiDimUncorrelatedEstimator(int64_t n, int ndim, const double x[], double average[], double error[]) { UncorrelatedEstimator(n, ndim, x, average, error); }
 inline void MultiDimFCBlockerEstimator(int64_t n, int ndim, const double x[], double average[], double error[]) { FCBlockerEstimator(n, ndim, x, average, error); }
 inline void OneDimUncorrelatedEstimator(int64_t n, const double x[], double & average, double & error) { UncorrelatedEstimator(n, 1, x, &average, &error); }
+inline void MultiDimBlockEstimator(int64_t n, int ndim, const double x[], int64_t nblocks, double average[], double error[]) { detail::check(mcig_estimate_blocks(n, ndim, x, nblocks, average, error)); }
+inline void OneDimBlockEstimator(int64_t n, const double x[], int64_t nblocks, double & average, double & error) { detail::check(mcig_estimate_blocks(n, 1, x, nblocks, &average, &error)); }
 inline void OneDimFCBlockerEstimator(int64_t n, const double x[], double & average, double & error) { FCBlockerEstimator(n, 1, x, &average, &error); }
 } // namespace mci
 #endif

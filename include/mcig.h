@@ -171,6 +171,9 @@ int mcig_get_phase_timings(mcig_ctx * ctx, double * find_ms, double * decorr_ms,
 
 /* ---- estimators on host data (include/mci/Estimators.hpp:9-45): data x[n][ndim], run on the device */
 int mcig_estimate(int estim_type, int64_t n, int ndim, const double * x, double * average, double * error);
+/* One/MultiDimBlockEstimator(n, [ndim,] x, nblocks, avg, err)  include/mci/Estimators.hpp:12, :30; src/Estimators.cpp:59-80, 158-185:
+ * means of nblocks consecutive blocks of n/nblocks samples (remainder ignored), then the uncorrelated estimator over them */
+int mcig_estimate_blocks(int64_t n, int ndim, const double * x, int64_t nblocks, double * average, double * error);
 
 /* ---- engine knobs without reference analogue */
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */

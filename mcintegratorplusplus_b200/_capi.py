@@ -65,6 +65,7 @@ SIGNATURES = {
     "mcig_get_timings": (C.c_int, [_ctx, _dp, _dp, _dp, _i64p]),
     "mcig_get_phase_timings": (C.c_int, [_ctx, _dp, _dp, _dp]),
     "mcig_estimate": (C.c_int, [C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp]),
+    "mcig_estimate_blocks": (C.c_int, [C.c_int64, C.c_int, _dp, C.c_int64, _dp, _dp]),
     "mcig_set_block_size": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_state_placement": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_dynamic_scheduling": (C.c_int, [_ctx, C.c_int]),

@@ -367,6 +367,28 @@ __global__ void mean_from_sum_kernel(const double * __restrict__ sums, i64 ncol,
     if (col < ncol) { mean[col] = sums[col]/n; }
 }
 
+// Fixed-block estimator, first half (One/MultiDimBlockEstimator, src/Estimators.cpp:59-80, 158-185): block means
+// av[b][col] = (sum of the nper samples of block b, left to right) * (1./nper); the uncorrelated estimator then runs over av.
+// One thread per (column, block): every block sum has the reference's order.
+__global__ void block_means_kernel(const double * __restrict__ data, i64 nper, i64 ncol, i64 nblocks, double * __restrict__ av)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    const i64 b = (i64)blockIdx.y;
+    if (col >= ncol || b >= nblocks) { return; }
+    const double * src = data + b*nper*ncol + col;
+    double s = 0.;
+    i64 i = 0;
+    for (; i + 8 <= nper; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { v[u] = __ldcs(src + (i + u)*ncol); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s = __dadd_rn(s, v[u]); }
+    }
+    for (; i < nper; ++i) { s = __dadd_rn(s, __ldcs(src + i*ncol)); }
+    av[b*ncol + col] = __dmul_rn(s, 1./(double)nper);
+}
+
 // ---------------------------------------------------------------------------------------------- K5 FCBlocker
 // One thread per chain, ONE pass over the series feeding all 45 block partitions (6..50 blocks) at once; block means are
 // pushed into the uncorrelated estimator's running sums in block order, so every sum has the reference's order.

@@ -370,6 +370,16 @@ def estimate(estim_type, x):
     return avg, err
 
 
+def estimate_blocks(x, nblocks):
+    """One/MultiDimBlockEstimator (include/mci/Estimators.hpp:12, :30): fixed number of blocks, then the uncorrelated estimator."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n, ndim = (x.shape[0], 1) if x.ndim == 1 else x.shape
+    avg = np.zeros(ndim)
+    err = np.zeros(ndim)
+    _capi.check(_capi.lib().mcig_estimate_blocks(n, ndim, x.ctypes.data_as(_dp), int(nblocks), avg.ctypes.data_as(_dp), err.ctypes.data_as(_dp)))
+    return avg, err
+
+
 def measure_peaks(device=0):
     d, i = C.c_double(), C.c_double()
     _capi.check(_capi.lib().mcig_measure_peaks(int(device), C.byref(d), C.byref(i)))

@@ -229,6 +229,10 @@ static void test_gpu()
         MJBlockerEstimator(4096, 1, x.data(), a2, e2);
         assert(fabs(a1 - a2[0]) < 1e-14 && e1 > 0. && e2[0] > 0.);
         assert(throws<std::invalid_argument>([&] { MJBlockerEstimator(1000, 1, x.data(), a2, e2); }));
+        double a3, e3;
+        OneDimBlockEstimator(4096, x.data(), 16, a3, e3); // 16 blocks of 256 samples
+        assert(fabs(a3 - a1) < 1e-14 && e3 > 0.);
+        assert(throws<std::invalid_argument>([&] { OneDimBlockEstimator(10, x.data(), 11, a3, e3); }));
     }
     std::cout << "gpu ok" << std::endl;
 }

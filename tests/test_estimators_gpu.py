@@ -26,6 +26,20 @@ def test_estimators_match_reference(wname, mcig, oracle, golden_est):
         assert np.allclose(err, ge, rtol=1e-9, atol=1e-18), (ename, err, ge)
 
 
+@pytest.mark.parametrize("wname", sorted(configs.WALKS))
+def test_fixed_block_estimator_matches_reference(wname, mcig, oracle, golden_est):
+    """One/MultiDimBlockEstimator (src/Estimators.cpp:59-80, 158-185) with the block count of the goldens (n/16 blocks)."""
+    pdf, nmc, ndim, step, cp, seed = configs.WALKS[wname]
+    datax, _, _, _, _ = oracle.testwalk(pdf, nmc, ndim, step, cp, seed)
+    x = datax if ndim > 1 else datax[:, 0]
+    g = golden_est[wname]["block16"]
+    avg, err = mcig.estimate_blocks(x, nmc//16)
+    assert np.allclose(avg, fromhex(g["avg"]), rtol=1e-12, atol=1e-15) and np.allclose(err, fromhex(g["err"]), rtol=1e-9, atol=1e-18)
+    from mcintegratorplusplus_b200._capi import McigError
+    with pytest.raises(McigError, match="n must be >= nblocks"):
+        mcig.estimate_blocks(x[:10], 11)
+
+
 def test_mjblocker_large_power_of_two_segments(mcig, oracle):
     """A series long enough to be time-split into segments (the HBM-streaming path) against the oracle's 13-pass algorithm."""
     rng = np.random.default_rng(7)
