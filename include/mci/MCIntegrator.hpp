@@ -56,6 +56,7 @@ private:
     std::unique_ptr<StepCallbackInterface> _cback; // device-functor replacement of the reference's std::function _cback
     int64_t _cbackDoubles{0};
     std::mt19937_64 _hostgen; // only for newRandomX()/moveX() (manual position helpers)
+    mutable std::vector<double> _xcache; // backing store of getX() const
 
     static int toSrrd(SRRDType t)
     {
@@ -331,6 +332,12 @@ public:
         std::vector<double> x(static_cast<size_t>(_ndim));
         detail::check(mcig_get_x(_ctx, 0, x.data()));
         return x[static_cast<size_t>(i)];
+    }
+    const double * getX() const // walker 0, as the reference's pointer to its xold (valid until the next call on this object)
+    {
+        _xcache.resize(static_cast<size_t>(_ndim));
+        detail::check(mcig_get_x(_ctx, 0, _xcache.data()));
+        return _xcache.data();
     }
     void getX(double x[], int64_t walker = 0) const { detail::check(mcig_get_x(_ctx, walker, x)); }
     double getMRT2Step(int i) const { return (i < _trialMove->getNStepSizes()) ? _trialMove->getStepSize(i) : 0.; }

@@ -83,7 +83,7 @@ public:
 };
 
 // all-particle move with a symmetric real-valued random distribution (include/mci/SRRDAllMove.hpp)
-class SRRDAllMove final: public TypedMoveInterface
+class SRRDAllMove: public TypedMoveInterface
 {
     TrialMoveInterface * _clone() const final { return new SRRDAllMove(*this); }
 
@@ -96,7 +96,7 @@ public:
 };
 
 // single-vector move (include/mci/SRRDVecMove.hpp)
-class SRRDVecMove final: public TypedMoveInterface
+class SRRDVecMove: public TypedMoveInterface
 {
     const int _nvecs, _veclen;
     TrialMoveInterface * _clone() const final { return new SRRDVecMove(*this); }
@@ -123,6 +123,38 @@ public:
 // run-time tag here (default uniform), so UniformAllMove(ndim, step) / UniformVecMove(nvecs, veclen, step) construct as in the reference
 using UniformAllMove = SRRDAllMove;
 using UniformVecMove = SRRDVecMove;
+
+// the other named instantiations (include/mci/SRRDAllMove.hpp:85-95, SRRDVecMove.hpp:101-111): same constructors, distribution fixed by the type
+template <SRRDType T>
+struct SRRDAllMoveOf final: public SRRDAllMove
+{
+    SRRDAllMoveOf(int ndim, double initStepSize): SRRDAllMove(ndim, initStepSize, T) {}
+    SRRDAllMoveOf(int ndim, int ntypes, const int typeEnds[], double initStepSize): SRRDAllMove(ndim, ntypes, typeEnds, initStepSize, T) {}
+};
+template <SRRDType T>
+struct SRRDVecMoveOf final: public SRRDVecMove
+{
+    SRRDVecMoveOf(int nvecs, int veclen, double initStepSize): SRRDVecMove(nvecs, veclen, initStepSize, T) {}
+    SRRDVecMoveOf(int nvecs, int veclen, int ntypes, const int typeEnds[], double initStepSize): SRRDVecMove(nvecs, veclen, ntypes, typeEnds, initStepSize, T) {}
+};
+using GaussianAllMove = SRRDAllMoveOf<SRRDType::Gaussian>;
+using StudentAllMove = SRRDAllMoveOf<SRRDType::Student>;
+using CauchyAllMove = SRRDAllMoveOf<SRRDType::Cauchy>;
+using ExponentialAllMove = SRRDAllMoveOf<SRRDType::Exponential>;
+using GammaAllMove = SRRDAllMoveOf<SRRDType::Gamma>;
+using WeibullAllMove = SRRDAllMoveOf<SRRDType::Weibull>;
+using LognormalAllMove = SRRDAllMoveOf<SRRDType::Lognormal>;
+using ChisqAllMove = SRRDAllMoveOf<SRRDType::Chisq>;
+using FisherAllMove = SRRDAllMoveOf<SRRDType::Fisher>;
+using GaussianVecMove = SRRDVecMoveOf<SRRDType::Gaussian>;
+using StudentVecMove = SRRDVecMoveOf<SRRDType::Student>;
+using CauchyVecMove = SRRDVecMoveOf<SRRDType::Cauchy>;
+using ExponentialVecMove = SRRDVecMoveOf<SRRDType::Exponential>;
+using GammaVecMove = SRRDVecMoveOf<SRRDType::Gamma>;
+using WeibullVecMove = SRRDVecMoveOf<SRRDType::Weibull>;
+using LognormalVecMove = SRRDVecMoveOf<SRRDType::Lognormal>;
+using ChisqVecMove = SRRDVecMoveOf<SRRDType::Chisq>;
+using FisherVecMove = SRRDVecMoveOf<SRRDType::Fisher>;
 
 // MultiStepMove (include/mci/MultiStepMove.hpp:21-84, src/MultiStepMove.cpp:6-47): mini-Metropolis of nsteps sub-moves driven by
 // the move's own sampling functions; default sub-move = uniform single-index move with step 0.05, default nsteps = ndim.

@@ -88,6 +88,7 @@ static void test_api()
     double x[3] = {5., -5., 10.};
     mci.setX(x);
     assert(mci.getX(0) == 5. && mci.getX(1) == -5. && mci.getX(2) == 10.);
+    assert(mci.getX()[2] == 10.);
     mci.setX(1, 2.5);
     assert(mci.getX(1) == 2.5);
     mci.setIRange(-1., 1.); // periodic wrap of the current position
@@ -124,6 +125,10 @@ static void test_api()
     mci.setTrialMove(SRRDType::Gaussian);
     assert(mci.getTrialMove().getSRRDType() == SRRDType::Gaussian);
     assert(throws<std::invalid_argument>([] { selectEstimatorType(true, false); }));
+    mci.setTrialMove(GaussianVecMove(3, 1, 0.4)); // named instantiations (include/mci/SRRDVecMove.hpp:101-111)
+    assert(mci.getTrialMove().getSRRDType() == SRRDType::Gaussian && mci.getTrialMove().getMoveType() == MoveType::Vec && mci.getMRT2Step(0) == 0.4);
+    mci.setTrialMove(FisherAllMove(3, 0.2));
+    assert(mci.getTrialMove().getSRRDType() == SRRDType::Fisher && mci.getTrialMove().getMoveType() == MoveType::All);
     MultiStepMove msm(3);
     assert(msm.getNSteps() == 3 && msm.getChangeRate() == 1.);
     assert(throws<std::invalid_argument>([&] { msm.addSamplingFunction(Exp1DPDF()); }));
