@@ -246,10 +246,17 @@ __global__ void __launch_bounds__(128) mj_segments_tiled_kernel(const double * _
     double t = 0.;
     const double * src = data + seg*L*ncol + col;
     const i64 ntiles = L >> T;
+    double nxt[TS]; // software prefetch: the loads of tile t+1 are in flight while tile t runs through its ~200 dependent FP64 operations
+#pragma unroll
+    for (int i = 0; i < TS; ++i) { nxt[i] = __ldcs(src + (i64)i*ncol); }
     for (i64 tile = 0; tile < ntiles; ++tile) {
         double v[TS];
 #pragma unroll
-        for (int i = 0; i < TS; ++i) { v[i] = __ldcs(src + (tile*TS + i)*ncol); }
+        for (int i = 0; i < TS; ++i) { v[i] = nxt[i]; }
+        if (tile + 1 < ntiles) {
+#pragma unroll
+            for (int i = 0; i < TS; ++i) { nxt[i] = __ldcs(src + ((tile + 1)*TS + i)*ncol); }
+        }
         int n = TS;
 #pragma unroll
         for (int k = 0; k < T; ++k) {
