@@ -56,6 +56,9 @@ namespace mcig_builtin {
 
 using mcig::exp;
 
+// 1/3 as a constant-bank operand (a 64-bit immediate costs two UMOV per use, re-materialised inside the walk loop)
+__constant__ double c_third = 1./3.;
+
 // ---------------------------------------------------------------- sampling functions
 struct ThreeDimGaussianPDF { // TestMCIFunctions.hpp:123-148 (ndim 3, nproto 1)
     static constexpr int NPAR = 0;
@@ -243,7 +246,7 @@ struct XSquared { // TestMCIFunctions.hpp:260-275
     static constexpr int NPAR = 0;
     const double * par;
     template <class X, class O>
-    MCIG_DEV void observableFunction(const X & in, O & out) const { out[0] = (in[0]*in[0] + in[1]*in[1] + in[2]*in[2])*(1./3.); }
+    MCIG_DEV void observableFunction(const X & in, O & out) const { out[0] = (in[0]*in[0] + in[1]*in[1] + in[2]*in[2])*c_third; }
 };
 
 struct GaussXSquared { // TestMCIFunctions.hpp:278-296
