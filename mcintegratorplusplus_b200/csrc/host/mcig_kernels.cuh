@@ -26,7 +26,15 @@ __global__ void reduce_u64_kernel(const u64 * __restrict__ in, i64 n, u64 * __re
 { // single block, deterministic
     __shared__ u64 sm[32];
     u64 s = 0;
-    for (i64 i = threadIdx.x; i < n; i += blockDim.x) { s += in[i]; }
+    i64 i = threadIdx.x;
+    for (; i + 7*(i64)blockDim.x < n; i += 8*(i64)blockDim.x) { // 8 loads in flight per thread (a single block: latency, not bandwidth)
+        u64 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { v[u] = in[i + u*(i64)blockDim.x]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s += v[u]; }
+    }
+    for (; i < n; i += blockDim.x) { s += in[i]; }
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); }
     if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = s; }
     __syncthreads();
@@ -66,7 +74,22 @@ __global__ void combine_walkers_kernel(const double * __restrict__ wavg, const d
     const int j = blockIdx.x;
     __shared__ double sm[3][32];
     double a = 0., e = 0., q = 0.;
-    for (i64 w = threadIdx.x; w < W; w += blockDim.x) {
+    i64 w = threadIdx.x;
+    for (; w + 3*(i64)blockDim.x < W; w += 4*(i64)blockDim.x) { // 8 loads in flight per thread, added in a fixed order
+        double v[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = wavg[(i64)j*W + w + u*(i64)blockDim.x];
+            r[u] = werr[(i64)j*W + w + u*(i64)blockDim.x];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a += v[u];
+            e += r[u]*r[u];
+            q += v[u]*v[u];
+        }
+    }
+    for (; w < W; w += blockDim.x) {
         const double v = wavg[(i64)j*W + w], r = werr[(i64)j*W + w];
         a += v;
         e += r*r;
@@ -261,16 +284,19 @@ __global__ void __launch_bounds__(128) mj_segments_tiled_kernel(const double * _
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             // level k holds n = TS >> k elements in v[0..n)
+            // sums of squares / lagged products with fused multiply-adds: one rounding per term instead of two (the reference's
+            // separately rounded products differ by <= 1 ulp per term, far inside the 1e-9 estimator tolerance) and 40 % fewer
+            // FP64 instructions per tile
             double X0 = __dadd_rn(v[0], -mu);
             if (tile == 0) { firstX[k] = X0; }
-            else { cr[k] = __dadd_rn(cr[k], __dmul_rn(prevX[k], X0)); }
-            sq[k] = __dadd_rn(sq[k], __dmul_rn(X0, X0));
+            else { cr[k] = fma(prevX[k], X0, cr[k]); }
+            sq[k] = fma(X0, X0, sq[k]);
             double Xp = X0;
 #pragma unroll
             for (int i = 1; i < (TS >> k); ++i) {
                 const double X = __dadd_rn(v[i], -mu);
-                sq[k] = __dadd_rn(sq[k], __dmul_rn(X, X));
-                cr[k] = __dadd_rn(cr[k], __dmul_rn(Xp, X));
+                sq[k] = fma(X, X, sq[k]);
+                cr[k] = fma(Xp, X, cr[k]);
                 Xp = X;
             }
             prevX[k] = Xp;
@@ -307,9 +333,29 @@ __constant__ double c_mj_quantile[64] = {
     61.656233, 62.829620, 64.001112, 65.170769, 66.338649, 67.504807, 68.669294, 69.832160, 70.993453, 72.153216, 73.311493,
     74.468324, 75.623748, 76.777803, 77.930524, 79.081944, 80.232098, 81.381015, 82.528727, 83.675261};
 
-// One thread per chain: merges the per-segment statistics (levels < m), runs the pyramid over the nseg segment tops
-// (levels >= m), then the test statistic / level choice of src/MJBlocker.cpp:106-152.
-__global__ void mj_finish_kernel(const double * __restrict__ seg_out, const double * __restrict__ top, i64 ncol, i64 n, i64 nseg, int m, int npow,
+// One thread per (chain, level < m): merges the per-segment statistics of that level in segment order -> lvl[(2k + {0,1})*ncol + col] = var_k, gamma_k
+__global__ void mj_merge_kernel(const double * __restrict__ seg_out, i64 ncol, i64 n, i64 nseg, int m, double * __restrict__ lvl)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    const int k = (int)blockIdx.y;
+    double sq = 0., cr = 0., lastX = 0.;
+    for (i64 s = 0; s < nseg; ++s) {
+        const double * o = seg_out + ((s*m + k)*4)*ncol + col;
+        const double o0 = __ldcs(o), o1 = __ldcs(o + ncol), o2 = __ldcs(o + 2*ncol), o3 = __ldcs(o + 3*ncol);
+        if (s > 0) { cr = __dadd_rn(cr, __dmul_rn(lastX, o2)); } // product across the segment border
+        sq = __dadd_rn(sq, o0);
+        cr = __dadd_rn(cr, o1);
+        lastX = o3;
+    }
+    const double nred = (double)(n >> k);
+    lvl[(i64)(2*k)*ncol + col] = sq/nred;
+    lvl[(i64)(2*k + 1)*ncol + col] = cr/nred;
+}
+
+// One thread per chain: levels < m from mj_merge_kernel, the pyramid over the nseg segment tops (levels >= m), then the test
+// statistic / level choice of src/MJBlocker.cpp:106-152.
+__global__ void mj_finish_kernel(const double * __restrict__ lvl, const double * __restrict__ top, i64 ncol, i64 n, i64 nseg, int m, int npow,
                                  const double * __restrict__ mean, double * __restrict__ wavg, double * __restrict__ werr)
 {
     const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
@@ -317,17 +363,8 @@ __global__ void mj_finish_kernel(const double * __restrict__ seg_out, const doub
     double var[MCIG_MJ_MAXLEV], gam[MCIG_MJ_MAXLEV];
     const double mu = mean[col];
     for (int k = 0; k < m; ++k) {
-        double sq = 0., cr = 0., lastX = 0.;
-        for (i64 s = 0; s < nseg; ++s) {
-            const double * o = seg_out + ((s*m + k)*4)*ncol + col;
-            if (s > 0) { cr = __dadd_rn(cr, __dmul_rn(lastX, o[2*ncol])); } // product across the segment border
-            sq = __dadd_rn(sq, o[0]);
-            cr = __dadd_rn(cr, o[ncol]);
-            lastX = o[3*ncol];
-        }
-        const double nred = (double)(n >> k);
-        var[k] = sq/nred;
-        gam[k] = cr/nred;
+        var[k] = lvl[(i64)(2*k)*ncol + col];
+        gam[k] = lvl[(i64)(2*k + 1)*ncol + col];
     }
     {
         MJLevel lv[MCIG_MJ_MAXLEV];
@@ -425,16 +462,28 @@ template <class OnBorder>
 __device__ __forceinline__ void fc_stream(const double * __restrict__ src, i64 ncol, i64 r0, i64 r1, i64 & next, double & run, OnBorder && on_border)
 {
     i64 i = r0;
-    for (; i + 16 <= r1; i += 16) {
-        double v[16];
+    if (i + 16 <= r1) {
+        double v[16], vn[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) { v[u] = __ldcs(src + (i + u)*ncol); }
-        if (next > i + 16) { run = __dadd_rn(run, fc_tree16(v)); }
-        else {
+        for (; i + 16 <= r1; i += 16) {
+            // the next batch is requested before this one is consumed: 32 loads in flight per thread while the adds below run
+            const bool more = (i + 32 <= r1);
+            if (more) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                run = __dadd_rn(run, v[u]);
-                if (i + u + 1 == next) { on_border(run); }
+                for (int u = 0; u < 16; ++u) { vn[u] = __ldcs(src + (i + 16 + u)*ncol); }
+            }
+            if (next > i + 16) { run = __dadd_rn(run, fc_tree16(v)); }
+            else {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    run = __dadd_rn(run, v[u]);
+                    if (i + u + 1 == next) { on_border(run); }
+                }
+            }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { v[u] = vn[u]; }
             }
         }
     }
@@ -546,14 +595,16 @@ __global__ void __launch_bounds__(32) fcblocker_smem_kernel(const double * __res
 // Event-driven FCBlocker for long series: ONE streaming pass with a single running sum per chain. The (position, partition)
 // pairs at which some partition completes a block are precomputed on the host and sorted by position (<= 1260 events);
 // a block sum is the difference of the running sum at its two borders. Per sample the thread does one add and one compare,
-// so the kernel streams at HBM speed; the 45 partitions' state (3 doubles each) is touched only at events.
+// so the kernel streams at HBM speed; the running sum at every event is written out (1260 doubles per chain) and the 45
+// partitions' statistics are formed from them by a second, partition-parallel pass.
 // Block sums obtained as prefix differences differ from the reference's direct sums by O(1e-16 * |prefix|/|block sum|)
 // relative — far inside the 1e-9 estimator tolerance; series up to MCIG_FC_EXACT_MAX samples use the exact kernel above.
-// Few long chains (ncol threads would leave the GPU empty): split every chain into nseg time segments. Pass 1 streams segment
-// (seg, col) and records the LOCAL running sum at every block border inside it plus the segment total; pass 2 walks the <= 1260
-// events of a chain in order with global prefix = (sum of earlier segment totals) + local prefix.
-__global__ void fc_split_prefix_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nseg, const i64 * __restrict__ ev_pos, int nev,
-                                       double * __restrict__ ev_prefix /*[nev][ncol]*/, double * __restrict__ seg_total /*[nseg][ncol]*/)
+// Chains are split into nseg time segments until the grid fills the machine. Pass 1 streams segment (seg, col) and records the
+// LOCAL running sum at every block border inside it plus the segment total; pass 2 uses global prefix = (sum of earlier segment
+// totals) + local prefix.
+__global__ void fc_split_prefix_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nseg, const i64 * __restrict__ ev_pos, const int * __restrict__ ev_slot,
+                                       int nev, double * __restrict__ ev_prefix /*[nev][ncol], row = ev_slot[event]: partition-major*/,
+                                       double * __restrict__ seg_total /*[nseg][ncol]*/)
 {
     const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
     const int seg = (int)blockIdx.y;
@@ -574,7 +625,7 @@ __global__ void fc_split_prefix_kernel(const double * __restrict__ data, i64 n, 
     fc_stream(data + col, ncol, r0, r1, next, run, [&](double r) {
         const i64 pos = next;
         while (next == pos) {
-            ev_prefix[(i64)e*ncol + col] = r;
+            __stcs(ev_prefix + (i64)ev_slot[e]*ncol + col, r);
             ++e;
             next = (e < nev) ? ev_pos[e] : n + 1;
         }
@@ -582,82 +633,71 @@ __global__ void fc_split_prefix_kernel(const double * __restrict__ data, i64 n, 
     seg_total[(i64)seg*ncol + col] = run;
 }
 
-__global__ void fc_split_finish_kernel(i64 n, i64 ncol, int nseg, int nobs_is_one, const i64 * __restrict__ ev_pos, const int * __restrict__ ev_part, int nev,
-                                       const double * __restrict__ ev_prefix, const double * __restrict__ seg_total, double * __restrict__ wavg,
-                                       double * __restrict__ werr)
+// exclusive scan of the segment totals per chain, in place: seg_total[s][col] becomes the sum of the segments before s
+__global__ void fc_seg_scan_kernel(i64 ncol, int nseg, double * __restrict__ seg_total)
 {
     const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
     if (col >= ncol) { return; }
-    constexpr int MINB = 6, NAV = 45;
-    double last[NAV], s1[NAV], s2[NAV];
-    for (int a = 0; a < NAV; ++a) { last[a] = 0.; s1[a] = 0.; s2[a] = 0.; }
-    const i64 len = (n + nseg - 1)/nseg;
     double base = 0.;
-    int seg = 0;
-    for (int e = 0; e < nev; ++e) {
-        const i64 pos = ev_pos[e];
-        const int sg = (int)((pos - 1)/len); // segment holding row pos-1, the last row inside the prefix
-        while (seg < sg) { base = __dadd_rn(base, seg_total[(i64)seg*ncol + col]); ++seg; }
-        const double run = __dadd_rn(base, ev_prefix[(i64)e*ncol + col]);
-        const int a = ev_part[e];
-        const double nper = (double)(n/(a + MINB));
-        const double av = __dmul_rn(__dadd_rn(run, -last[a]), 1./nper);
-        last[a] = run;
-        s1[a] = __dadd_rn(s1[a], av);
-        s2[a] = __dadd_rn(s2[a], __dmul_rn(av, av));
+    for (int sg = 0; sg < nseg; ++sg) {
+        const double t = seg_total[(i64)sg*ncol + col];
+        seg_total[(i64)sg*ncol + col] = base;
+        base = __dadd_rn(base, t);
+    }
+}
+
+// Pass 2, one thread per (chain, partition): the prefixes at the block borders of partition a are the rows off(a) .. off(a) + nb - 1
+// of ev_prefix (the streaming pass writes them partition-major); a block sum is the difference of the global prefix = segment base
+// + local prefix at its two borders. Scalar state only (a single thread walking all 1260 events of a chain needs 45 dynamically
+// indexed accumulator triples, i.e. local memory: measured 1.0 GB of extra DRAM writes on an 8.6 GB series).
+__global__ void fc_part_stats_kernel(i64 n, i64 ncol, const int * __restrict__ seg_of_slot, const double * __restrict__ ev_prefix,
+                                     const double * __restrict__ seg_base, double * __restrict__ stats /*[45][2][ncol]*/)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    constexpr int MINB = 6;
+    const int a = (int)blockIdx.y;
+    const int nb = a + MINB;
+    const int off = MINB*a + a*(a - 1)/2; // sum of the block counts of the partitions before a
+    const double rnper = 1./(double)(n/nb);
+    double last = 0., s1 = 0., s2 = 0.;
+    int j = 0;
+    for (; j + 4 <= nb; j += 4) { // loads of four borders in flight; the adds keep the block order
+        double run[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            run[u] = __dadd_rn(seg_base[(i64)seg_of_slot[off + j + u]*ncol + col], __ldcs(ev_prefix + (i64)(off + j + u)*ncol + col));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double av = __dmul_rn(__dadd_rn(run[u], -last), rnper);
+            last = run[u];
+            s1 = __dadd_rn(s1, av);
+            s2 = __dadd_rn(s2, __dmul_rn(av, av));
+        }
+    }
+    for (; j < nb; ++j) {
+        const double run = __dadd_rn(seg_base[(i64)seg_of_slot[off + j]*ncol + col], __ldcs(ev_prefix + (i64)(off + j)*ncol + col));
+        const double av = __dmul_rn(__dadd_rn(run, -last), rnper);
+        last = run;
+        s1 = __dadd_rn(s1, av);
+        s2 = __dadd_rn(s2, __dmul_rn(av, av));
+    }
+    stats[(i64)(2*a)*ncol + col] = s1;
+    stats[(i64)(2*a + 1)*ncol + col] = s2;
+}
+
+__global__ void fc_final_kernel(i64 ncol, int nobs_is_one, const double * __restrict__ stats, double * __restrict__ wavg, double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    constexpr int NAV = 45;
+    double s1[NAV], s2[NAV];
+    for (int a = 0; a < NAV; ++a) {
+        s1[a] = stats[(i64)(2*a)*ncol + col];
+        s2[a] = stats[(i64)(2*a + 1)*ncol + col];
     }
     fc_finish(s1, s2, nobs_is_one, wavg[col], werr[col]);
-}
-__global__ void fcblocker_events_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, const i64 * __restrict__ ev_pos,
-                                        const int * __restrict__ ev_part, int nev, double * __restrict__ wavg, double * __restrict__ werr)
-{
-    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
-    if (col >= ncol) { return; }
-    constexpr int MINB = 6, MAXB = 50, NAV = MAXB - MINB + 1, MPA = 4, NACCD = NAV - 2*MPA;
-    double last[NAV], s1[NAV], s2[NAV];
-    for (int a = 0; a < NAV; ++a) { last[a] = 0.; s1[a] = 0.; s2[a] = 0.; }
-    double run = 0.;
-    int e = 0;
-    i64 next = (nev > 0) ? ev_pos[0] : n + 1;
-    // rows after the last block border are ignored by every partition (Estimators.cpp:65, :164)
-    const i64 last_border = (nev > 0) ? ev_pos[nev - 1] : 0;
-    fc_stream(data + col, ncol, 0, last_border, next, run, [&](double r) {
-        const i64 pos = next;
-        while (next == pos) { // a block of partition a ends after sample pos-1
-            const int a = ev_part[e];
-            const double nper = (double)(n/(a + MINB));
-            const double av = __dmul_rn(__dadd_rn(r, -last[a]), 1./nper);
-            last[a] = r;
-            s1[a] = __dadd_rn(s1[a], av);
-            s2[a] = __dadd_rn(s2[a], __dmul_rn(av, av));
-            ++e;
-            next = (e < nev) ? ev_pos[e] : n + 1;
-        }
-    });
-    double av[NAV], err[NAV];
-    for (int a = 0; a < NAV; ++a) {
-        const double nb = (double)(a + MINB);
-        const double norm = 1./nb;
-        const double mean = __dmul_rn(s1[a], norm);
-        double er = __dadd_rn(__dmul_rn(s2[a], norm), -__dmul_rn(mean, mean));
-        if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/(nb - 1.)) : sqrt(__dmul_rn(er, 1./(nb - 1.))); }
-        else { er = 0.; }
-        av[a] = mean;
-        err[a] = er;
-    }
-    double accd[NACCD];
-    for (int i2 = MPA; i2 < NACCD + MPA; ++i2) {
-        double acc = 0.;
-        for (int i1 = 1; i1 <= MPA; ++i1) { acc = __dadd_rn(acc, fc_err_delta(i1, err + i2)); }
-        accd[i2 - MPA] = acc;
-    }
-    int imin = 0;
-    for (int i2 = 1; i2 < NACCD; ++i2) {
-        if (fabs(accd[i2]) < fabs(accd[imin])) { imin = i2; }
-    }
-    imin += MPA;
-    wavg[col] = 0.2*(av[imin - 2] + av[imin - 1] + av[imin] + av[imin + 1] + av[imin + 2]);
-    werr[col] = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
 }
 
 // ---------------------------------------------------------------------------------------------- device-resident calibration

@@ -50,8 +50,12 @@ def c4_estimators(W=65536, npow=14):
         mci.addObservable(m.XSquared(), 1, 1, False, est)  # FullAccumulator
         mci.setMRT2Step(1.0)
         mci.integrate(nmc, False, False)
-        avg, err = mci.integrate(nmc, False, False)
-        t = mci.timings()
+        ts = []
+        for _ in range(7):  # best of 7: single runs of a 1.5 ms kernel scatter by several percent
+            avg, err = mci.integrate(nmc, False, False)
+            ts.append(mci.timings())
+        t = min(ts, key=lambda q: q["estim_ms"])
+        t["walk_ms"] = min(q["walk_ms"] for q in ts)
         nbytes = 8.0*nmc*W
         print(json.dumps({"config": "C4_estimators", "estimator": label, "walkers": W, "n_per_chain": nmc, "series_GB": nbytes/1e9,
                           "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "estim_GBps": nbytes/(t["estim_ms"]*1e-3)/1e9,
