@@ -251,25 +251,36 @@ __global__ void mj_segments_kernel(const double * __restrict__ data, i64 ncol, i
 // only the level-4 element (1/16 of the samples) enters the dynamic pyramid. Accumulation order per level is ascending in
 // the sample index, exactly as in the generic kernel and in the reference.
 #define MCIG_MJ_TILE_LOG 4
+#ifndef MCIG_MJ_MID
+#define MCIG_MJ_MID 2 // levels T .. T+MID-1 also live in registers (driven by the bits of the tile index); the dynamic pyramid sees 1/2^(T+MID) of the samples
+#endif
 __global__ void __launch_bounds__(128) mj_segments_tiled_kernel(const double * __restrict__ data, i64 ncol, i64 L, int m, const double * __restrict__ mean,
                                                                double * __restrict__ seg_out, double * __restrict__ top)
 {
-    constexpr int T = MCIG_MJ_TILE_LOG, TS = 1 << T;
+    constexpr int T = MCIG_MJ_TILE_LOG, TS = 1 << T, S = MCIG_MJ_MID;
     const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
     const i64 seg = blockIdx.y;
     if (col >= ncol) { return; }
     const double mu = mean[col];
-    double sq[T], cr[T], firstX[T], prevX[T];
+    double sq[T], cr[T], prevX[T];
 #pragma unroll
-    for (int k = 0; k < T; ++k) { sq[k] = 0.; cr[k] = 0.; firstX[k] = 0.; prevX[k] = 0.; }
+    for (int k = 0; k < T; ++k) { sq[k] = 0.; cr[k] = 0.; prevX[k] = 0.; }
+    // middle levels: the level-T element of tile t reaches level T+k iff the low k bits of t are all ones, and completes a pair there iff bit k
+    // is set too: warp-uniform branches on the tile index, statically named registers (the dynamically indexed pyramid below lives in local memory:
+    // with every tile pushing into it the kernel moved as many bytes through L1 as it streamed from HBM)
+    const int ms = (m - T < S) ? (m - T) : S; // middle levels in use
+    double msq[S > 0 ? S : 1], mcr[S > 0 ? S : 1], mprev[S > 0 ? S : 1], mpend[S > 0 ? S : 1];
+#pragma unroll
+    for (int k = 0; k < S; ++k) { msq[k] = 0.; mcr[k] = 0.; mprev[k] = 0.; mpend[k] = 0.; }
     MJLevel lv[MCIG_MJ_MAXLEV];
-    const int mu_lev = m - T; // levels handled by the dynamic pyramid
+    const int mu_lev = m - T - ms; // levels handled by the dynamic pyramid
     for (int k = 0; k < mu_lev; ++k) { lv[k].sq = 0.; lv[k].cr = 0.; lv[k].firstX = 0.; lv[k].prevX = 0.; lv[k].pend = 0.; }
     unsigned long long have = 0, cnt = 0;
     double t = 0.;
     const double * src = data + seg*L*ncol + col;
+    double * const o_first = seg_out + (seg*m*4 + 2)*ncol + col; // firstX of level k at o_first[k*4*ncol]: written when it occurs, not kept in registers
     const i64 ntiles = L >> T;
-    double nxt[TS]; // software prefetch: the loads of tile t+1 are in flight while tile t runs through its ~200 dependent FP64 operations
+    double nxt[TS]; // software prefetch: the loads of tile t+1 are in flight while tile t runs through its ~150 dependent FP64 operations
 #pragma unroll
     for (int i = 0; i < TS; ++i) { nxt[i] = __ldcs(src + (i64)i*ncol); }
     for (i64 tile = 0; tile < ntiles; ++tile) {
@@ -280,15 +291,14 @@ __global__ void __launch_bounds__(128) mj_segments_tiled_kernel(const double * _
 #pragma unroll
             for (int i = 0; i < TS; ++i) { nxt[i] = __ldcs(src + ((tile + 1)*TS + i)*ncol); }
         }
-        int n = TS;
 #pragma unroll
         for (int k = 0; k < T; ++k) {
-            // level k holds n = TS >> k elements in v[0..n)
+            // level k holds TS >> k elements in v[0..)
             // sums of squares / lagged products with fused multiply-adds: one rounding per term instead of two (the reference's
             // separately rounded products differ by <= 1 ulp per term, far inside the 1e-9 estimator tolerance) and 40 % fewer
             // FP64 instructions per tile
             double X0 = __dadd_rn(v[0], -mu);
-            if (tile == 0) { firstX[k] = X0; }
+            if (tile == 0) { o_first[(i64)k*4*ncol] = X0; }
             else { cr[k] = fma(prevX[k], X0, cr[k]); }
             sq[k] = fma(X0, X0, sq[k]);
             double Xp = X0;
@@ -302,21 +312,44 @@ __global__ void __launch_bounds__(128) mj_segments_tiled_kernel(const double * _
             prevX[k] = Xp;
 #pragma unroll
             for (int i = 0; i < (TS >> (k + 1)); ++i) { v[i] = __dmul_rn(0.5, __dadd_rn(v[2*i], v[2*i + 1])); }
-            n >>= 1;
         }
-        (void)n;
-        mj_push(lv, have, cnt, mu_lev, v[0], mu, t);
+        double x = v[0];
+        bool up = true; // x is an element of the next level
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            if (up && k < ms) {
+                const double X = __dadd_rn(x, -mu);
+                msq[k] = fma(X, X, msq[k]);
+                if (tile >= ((i64)1 << k)) { mcr[k] = fma(mprev[k], X, mcr[k]); }
+                else { o_first[(i64)(T + k)*4*ncol] = X; }
+                mprev[k] = X;
+                if ((tile >> k) & 1) { x = __dmul_rn(0.5, __dadd_rn(mpend[k], x)); }
+                else {
+                    mpend[k] = x;
+                    up = false;
+                }
+            }
+        }
+        if (up) { mj_push(lv, have, cnt, mu_lev, x, mu, t); }
     }
 #pragma unroll
     for (int k = 0; k < T; ++k) {
         double * o = seg_out + ((seg*m + k)*4)*ncol + col;
         o[0] = sq[k];
         o[ncol] = cr[k];
-        o[2*ncol] = firstX[k];
         o[3*ncol] = prevX[k];
     }
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        if (k < ms) {
+            double * o = seg_out + ((seg*m + T + k)*4)*ncol + col;
+            o[0] = msq[k];
+            o[ncol] = mcr[k];
+            o[3*ncol] = mprev[k];
+        }
+    }
     for (int k = 0; k < mu_lev; ++k) {
-        double * o = seg_out + ((seg*m + T + k)*4)*ncol + col;
+        double * o = seg_out + ((seg*m + T + ms + k)*4)*ncol + col;
         o[0] = lv[k].sq;
         o[ncol] = lv[k].cr;
         o[2*ncol] = lv[k].firstX;
