@@ -33,6 +33,7 @@ WALKERS_PER_GPU = 65536
 NMC = 100000
 FP64_INSTR_PER_STEP = 34   # 4 uniform conversions + 6 proposal + 3 proto + 1 exponent + 17 exp + 1 compare + 1 obs + 1 accumulate
 FLOP_PER_STEP = 53
+WALK_DRAM_BYTES_PER_LAUNCH = 1586176  # ncu dram__bytes_read.sum (+ 0 written) of one mcig_walk_dyn launch, profiles/r01_walk_r1f_dyn_ncu_raw.csv
 METRIC = "metropolis_samples_per_sec"
 WORKLOAD = "bench_throughput_3G: ThreeDimGaussianPDF ndim=3 + XSquared, uniform all-move step 1.0, SimpleAccumulator, 65536 walkers/GPU x 1e5 steps"
 
@@ -154,7 +155,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)  # 20 x 26 ms: long enough for the clock sampler to see the load
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,7 +279,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms/args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_issue", "achieved": achieved/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s", "frac": achieved/peaks[0],
-                         "traffic": None, "kernel": "mcig_walk (JIT-specialised Metropolis walk)", "kernel_ms_per_step": walk_ms_max/args.steps,
+                         "traffic": WALK_DRAM_BYTES_PER_LAUNCH, "traffic_note": "dram__bytes_read + dram__bytes_write of one walk launch (ncu --set full, profiles/r01_walk_r1f_dyn_ncu_raw.csv): the 1.5 MB of start positions, nothing written; the bound is FP64/ALU issue, not HBM",
+                         "kernel": "mcig_walk (JIT-specialised Metropolis walk)", "kernel_ms_per_step": walk_ms_max/args.steps,
                          "fp64_instr_per_metropolis_step": FP64_INSTR_PER_STEP, "flop_per_metropolis_step": FLOP_PER_STEP,
                          "achieved_tflops": FLOP_PER_STEP*steps_per_s_kernel/1e12, "peak_tflops": 2*peaks[0]/1e12,
                          "peak_source": "DFMA/s measured live by mcig_measure_peaks on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
