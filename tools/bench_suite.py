@@ -108,6 +108,8 @@ if __name__ == "__main__":
         c3_ndim("vec")
         c3_ndim("all")
         c3_ndim("multistep", ndims=(2, 4, 8, 16, 32))
+    if "c3ms" in which:
+        c3_ndim("multistep", ndims=(2, 4, 8, 16, 32, 64))
     if "c3all" in which:
         c3_ndim("all")
         c3_ndim("all", ndims=(128, 256, 1024), W=65536, nmc=1000)
