@@ -203,6 +203,7 @@ def main():
         return float(t.item())
 
     peaks = m.measure_peaks(local)
+    philox_peak = m.measure_philox_peak(local)  # Philox4x32-10 blocks/s with nothing else issued: one block per Metropolis step in this workload
     # ---- device-resident arm
     for _ in range(max(3, args.warmup)):
         mci.integrate(NMC, False, False)
@@ -285,6 +286,9 @@ def main():
                          "achieved_tflops": FLOP_PER_STEP*steps_per_s_kernel/1e12, "peak_tflops": 2*peaks[0]/1e12,
                          "peak_source": "DFMA/s measured live by mcig_measure_peaks on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                          "imad_peak_ginst": peaks[1]/1e9,
+                         "rng_bound": {"philox4x32_10_blocks_per_s": philox_peak, "blocks_per_step": 1, "frac": steps_per_s_kernel/philox_peak,
+                                       "note": "issue-rate bound of the counter RNG alone (20 IMAD.WIDE.U32 at a quarter of the FP32 rate per block), measured live; "
+                                               "the walk loop cannot exceed it whatever its FP64 content: context for the FP64 fraction above"},
                          "full_occupancy": None if full is None else {
                              "walkers": full[0], "steps_per_s": full[1], "frac": FP64_INSTR_PER_STEP*full[1]/peaks[0],
                              "note": "same kernel, 8 warps per scheduler instead of the workload's 3.46; context only, not the bench value"}},

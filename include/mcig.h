@@ -202,6 +202,8 @@ int mcig_prebuild(mcig_ctx * ctx);
 int64_t mcig_get_kernel_source(mcig_ctx * ctx, char * buf, int64_t cap);
 /* issue-rate microbenchmarks (roofline denominators): DFMA/s and IMAD/s of the current device */
 int mcig_measure_peaks(int device, double * dfma_per_s, double * imad_per_s);
+/* Philox4x32-10 blocks per second of the current device when nothing else is issued (the RNG's own issue-rate bound of the walk loop) */
+int mcig_measure_philox_peak(int device, double * blocks_per_s);
 
 #ifdef __cplusplus
 }

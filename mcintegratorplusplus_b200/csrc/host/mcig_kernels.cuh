@@ -850,4 +850,34 @@ __global__ void imad_peak_kernel(unsigned * out, int iters, unsigned a, unsigned
     if (s == 0x12345678u) { out[0] = s; }
 }
 
+// Philox4x32-10 blocks back to back (2 independent counters per thread): the issue rate of the RNG alone. One round = 2 IMAD.WIDE.U32 + 2 LOP3;
+// on sm_100a the 32x32->64 multiply issues at a quarter of the FP32 rate, so a block costs ~86 scheduler cycles per warp whatever else the loop does.
+__global__ void philox_peak_kernel(unsigned * out, int iters, unsigned k0, unsigned k1)
+{
+    unsigned c[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { c[j][0] = threadIdx.x; c[j][1] = j; c[j][2] = blockIdx.x; c[j][3] = 7u; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            unsigned ka = k0, kb = k1;
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const unsigned long long p0 = (unsigned long long)c[j][0]*0xD2511F53ull, p1 = (unsigned long long)c[j][2]*0xCD9E8D57ull;
+                const unsigned n0 = (unsigned)(p1 >> 32) ^ c[j][1] ^ ka, n2 = (unsigned)(p0 >> 32) ^ c[j][3] ^ kb;
+                c[j][1] = (unsigned)p1;
+                c[j][3] = (unsigned)p0;
+                c[j][0] = n0;
+                c[j][2] = n2;
+                ka += 0x9E3779B9u;
+                kb += 0xBB67AE85u;
+            }
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { s += c[j][0] ^ c[j][1] ^ c[j][2] ^ c[j][3]; }
+    if (s == 0x12345678u) { out[0] = s; }
+}
+
 } // namespace mcig_k

@@ -384,3 +384,10 @@ def measure_peaks(device=0):
     d, i = C.c_double(), C.c_double()
     _capi.check(_capi.lib().mcig_measure_peaks(int(device), C.byref(d), C.byref(i)))
     return d.value, i.value
+
+
+def measure_philox_peak(device=0):
+    """Philox4x32-10 blocks per second with nothing else in the loop: the RNG's own issue-rate bound (mcig_measure_philox_peak)."""
+    b = C.c_double()
+    _capi.check(_capi.lib().mcig_measure_philox_peak(int(device), C.byref(b)))
+    return b.value

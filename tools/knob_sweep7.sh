@@ -1,0 +1,12 @@
+#!/bin/bash
+run() {
+  echo "== defs='$1'"
+  MCIG_JIT_DEFINES="$1" python tools/profile_walk.py 100000 65536 0 1
+  MCIG_JIT_DEFINES="$1" python tools/profile_walk.py 100000 65536 512 0
+  MCIG_JIT_DEFINES="$1" python tools/profile_walk.py 100000 303104 256 0
+}
+run ""
+run "MCIG_SPLIT_GROUP=0"
+run "MCIG_WALK_UNROLL_DYN=2"
+run "MCIG_WALK_UNROLL=1"
+run "MCIG_NACC_ASM=1"
