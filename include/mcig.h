@@ -51,7 +51,8 @@ enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1, MCIG_PLUGIN_CALLBACK = 2 };
 /* plugin flags (sampling functions) */
 enum {
     MCIG_PLUGIN_HAS_UPDATE = 1,     /* functor overrides updatedAcceptance (selective update for single-vector moves) */
-    MCIG_PLUGIN_ELEMENTWISE = 2,    /* proto value k depends on x[k] only; updatedAcceptance touches protonew[changedIdx] only */
+    MCIG_PLUGIN_ELEMENTWISE = 2,    /* proto value k depends on x[k] only; updatedAcceptance touches protonew[changedIdx] only, by plain assignment /
+                                     * reads (with HAS_UPDATE the new values of a selective update may live in registers, not in an array) */
     MCIG_PLUGIN_LOG_ACCEPTANCE = 4, /* functor provides logAcceptance(protoold, protonew) = log(acceptanceFunction) */
     MCIG_PLUGIN_DEPENDENT = 8       /* observable: observableFunction(x, out, dep) with dep.proto(i) / dep.obs(k, j) (DependentObservableInterface) */
 };
