@@ -469,14 +469,15 @@ __global__ void block_means_kernel(const double * __restrict__ data, i64 nper, i
 // ---------------------------------------------------------------------------------------------- K5 FCBlocker
 // One thread per chain, ONE pass over the series feeding all 45 block partitions (6..50 blocks) at once; block means are
 // pushed into the uncorrelated estimator's running sums in block order, so every sum has the reference's order.
-__device__ __forceinline__ double fc_err_delta(int mode, const double * e /*centre element*/)
+template <class E>
+__device__ __forceinline__ double fc_err_delta(int mode, E e /* e(k): element at offset k from the centre */)
 { // calcErrDelta, src/Estimators.cpp:9-31
     switch (mode) {
-    case 1: return (-0.5*e[-1] + 0.5*e[1]);
-    case 2: return ((1./12.)*e[-2] - (2./3.)*e[-1] + (2./3.)*e[1] - (1./12.)*e[2]);
-    case 3: return (-(1./60.)*e[-3] + (3./20.)*e[-2] - 0.75*e[-1] + 0.75*e[1] - (3./20.)*e[2] + (1./60.)*e[3]);
+    case 1: return (-0.5*e(-1) + 0.5*e(1));
+    case 2: return ((1./12.)*e(-2) - (2./3.)*e(-1) + (2./3.)*e(1) - (1./12.)*e(2));
+    case 3: return (-(1./60.)*e(-3) + (3./20.)*e(-2) - 0.75*e(-1) + 0.75*e(1) - (3./20.)*e(2) + (1./60.)*e(3));
     default:
-        return ((1./280.)*e[-4] - (4./105.)*e[-3] + 0.2*e[-2] - 0.8*e[-1] + 0.8*e[1] - 0.2*e[2] + (4./105.)*e[3] - (1./280.)*e[4]);
+        return ((1./280.)*e(-4) - (4./105.)*e(-3) + 0.2*e(-2) - 0.8*e(-1) + 0.8*e(1) - 0.2*e(2) + (4./105.)*e(3) - (1./280.)*e(4));
     }
 }
 
@@ -526,74 +527,100 @@ __device__ __forceinline__ void fc_stream(const double * __restrict__ src, i64 n
     }
 }
 
-// Statistics of the 45 partitions -> plateau search -> 5-point averages (src/Estimators.cpp:82-122, 191-246)
-__device__ __forceinline__ void fc_finish(const double * s1, const double * s2, int nobs_is_one, double & out_avg, double & out_err)
+// Statistics of the 45 partitions -> plateau search -> 5-point averages (src/Estimators.cpp:82-122, 191-246). s1(a) / s2(a) give read-write access
+// to the partition sums and are overwritten with the partition means / errors (in place: the shared-memory variant keeps no per-thread arrays, and
+// the plateau score is tracked as a running minimum instead of an array)
+template <class A1, class A2>
+__device__ __forceinline__ void fc_finish_inplace(A1 s1, A2 s2, int nobs_is_one, double & out_avg, double & out_err)
 {
     constexpr int MINB = 6, MAXB = 50, NAV = MAXB - MINB + 1, MPA = 4, NACCD = NAV - 2*MPA;
-    double av[NAV], err[NAV];
     for (int a = 0; a < NAV; ++a) {
         const double nb = (double)(a + MINB);
         const double norm = 1./nb;
-        const double mean = __dmul_rn(s1[a], norm);
-        double er = __dadd_rn(__dmul_rn(s2[a], norm), -__dmul_rn(mean, mean));
+        const double mean = __dmul_rn(s1(a), norm);
+        double er = __dadd_rn(__dmul_rn(s2(a), norm), -__dmul_rn(mean, mean));
         if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/(nb - 1.)) : sqrt(__dmul_rn(er, 1./(nb - 1.))); }
         else { er = 0.; }
-        av[a] = mean;
-        err[a] = er;
-    }
-    double accd[NACCD];
-    for (int i2 = MPA; i2 < NACCD + MPA; ++i2) {
-        double acc = 0.;
-        for (int i1 = 1; i1 <= MPA; ++i1) { acc = __dadd_rn(acc, fc_err_delta(i1, err + i2)); }
-        accd[i2 - MPA] = acc;
+        s1(a) = mean;
+        s2(a) = er;
     }
     int imin = 0;
-    for (int i2 = 1; i2 < NACCD; ++i2) {
-        if (fabs(accd[i2]) < fabs(accd[imin])) { imin = i2; }
+    double best = 0.;
+    for (int i2 = MPA; i2 < NACCD + MPA; ++i2) {
+        double acc = 0.;
+        for (int i1 = 1; i1 <= MPA; ++i1) { acc = __dadd_rn(acc, fc_err_delta(i1, [&](int k) { return (double)s2(i2 + k); })); }
+        if (i2 == MPA || fabs(acc) < best) { // first minimum wins, as in the reference's strict comparison
+            best = fabs(acc);
+            imin = i2;
+        }
     }
-    imin += MPA;
-    out_avg = 0.2*(av[imin - 2] + av[imin - 1] + av[imin] + av[imin + 1] + av[imin + 2]);
-    out_err = 0.2*(err[imin - 2] + err[imin - 1] + err[imin] + err[imin + 1] + err[imin + 2]);
+    out_avg = 0.2*(s1(imin - 2) + s1(imin - 1) + s1(imin) + s1(imin + 1) + s1(imin + 2));
+    out_err = 0.2*(s2(imin - 2) + s2(imin - 1) + s2(imin) + s2(imin + 1) + s2(imin + 2));
 }
 
-// One pass per partition, as the reference does (45 passes, src/Estimators.cpp:207-213), with scalar state. A single pass feeding
-// all 45 partitions needs dynamically indexed per-partition state in local memory (measured 5x slower). Every block sum is
-// accumulated left to right from zero (the reference's order, bit for bit); four blocks of a partition are summed side by side
-// (independent chains: the adds of one chain are 4500 deep per thread) and pushed into the partition's sums in block order.
+__device__ __forceinline__ void fc_finish(double * s1, double * s2, int nobs_is_one, double & out_avg, double & out_err)
+{
+    fc_finish_inplace([&](int a) -> double & { return s1[a]; }, [&](int a) -> double & { return s2[a]; }, nobs_is_one, out_avg, out_err);
+}
+
+// Exact short-series path. The reference makes one pass per partition (45 passes, src/Estimators.cpp:207-213); a single pass feeding
+// all 45 partitions needs dynamically indexed per-partition state in local memory (measured 5x slower).
+// Partitions nb_lo..nb_hi share the block length nper = n/nb (for n = 100 the 45 partitions have 13 distinct block lengths): their block means are the
+// same sequence, partition nb uses its first nb terms. One pass per distinct block length therefore serves the whole group: the running sums
+// (t1, t2) are handed to out(partition index, t1, t2) after nb blocks for every nb of the group. Every block sum and both running sums are accumulated in
+// the reference's order (src/Estimators.cpp:59-76: blocks left to right, samples left to right), so the results are the reference's bit for bit;
+// four blocks are summed side by side because a single chain of dependent adds would leave the FP64 pipe idle.
+template <class LD, class OUT>
+__device__ __forceinline__ void fc_exact_group(i64 n, LD ld, int nb_lo, int nb_hi, OUT out)
+{
+    constexpr int MINB = 6;
+    const i64 nper = n/nb_lo;
+    const double rnper = 1./(double)nper;
+    double t1 = 0., t2 = 0.;
+    int j = 0;
+    for (; j + 4 <= nb_hi; j += 4) {
+        double b0 = 0., b1 = 0., b2 = 0., b3 = 0.;
+        const i64 o0 = (i64)j*nper, o1 = o0 + nper, o2 = o1 + nper, o3 = o2 + nper;
+#pragma unroll 2
+        for (i64 i = 0; i < nper; ++i) {
+            b0 = __dadd_rn(b0, ld(o0 + i));
+            b1 = __dadd_rn(b1, ld(o1 + i));
+            b2 = __dadd_rn(b2, ld(o2 + i));
+            b3 = __dadd_rn(b3, ld(o3 + i));
+        }
+        const double av[4] = {__dmul_rn(b0, rnper), __dmul_rn(b1, rnper), __dmul_rn(b2, rnper), __dmul_rn(b3, rnper)};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            t1 = __dadd_rn(t1, av[u]);
+            t2 = __dadd_rn(t2, __dmul_rn(av[u], av[u]));
+            if (j + u + 1 >= nb_lo) { out(j + u + 1 - MINB, t1, t2); }
+        }
+    }
+    for (; j < nb_hi; ++j) {
+        double bsum = 0.;
+        const i64 o = (i64)j*nper;
+        for (i64 i = 0; i < nper; ++i) { bsum = __dadd_rn(bsum, ld(o + i)); }
+        const double av = __dmul_rn(bsum, rnper);
+        t1 = __dadd_rn(t1, av);
+        t2 = __dadd_rn(t2, __dmul_rn(av, av));
+        if (j + 1 >= nb_lo) { out(j + 1 - MINB, t1, t2); }
+    }
+}
+
+// last partition (block count) that shares the block length of partition nb: n/nb' == n/nb  <=>  nb' <= n/(n/nb)
+__device__ __forceinline__ int fc_group_end(i64 n, int nb)
+{
+    const i64 hi = n/(n/nb);
+    return (hi < 50) ? (int)hi : 50;
+}
+
 template <class LD>
 __device__ __forceinline__ void fc_exact_passes(i64 n, LD ld, double * s1, double * s2)
 {
-    constexpr int MINB = 6, NAV = 45;
-    for (int a = 0; a < NAV; ++a) {
-        const int nb = a + MINB;
-        const i64 nper = n/nb;
-        const double rnper = 1./(double)nper;
-        double t1 = 0., t2 = 0.;
-        int j = 0;
-        for (; j + 4 <= nb; j += 4) {
-            double b0 = 0., b1 = 0., b2 = 0., b3 = 0.;
-            const i64 o0 = (i64)j*nper, o1 = o0 + nper, o2 = o1 + nper, o3 = o2 + nper;
-#pragma unroll 2
-            for (i64 i = 0; i < nper; ++i) {
-                b0 = __dadd_rn(b0, ld(o0 + i));
-                b1 = __dadd_rn(b1, ld(o1 + i));
-                b2 = __dadd_rn(b2, ld(o2 + i));
-                b3 = __dadd_rn(b3, ld(o3 + i));
-            }
-            const double a0 = __dmul_rn(b0, rnper), a1 = __dmul_rn(b1, rnper), a2 = __dmul_rn(b2, rnper), a3 = __dmul_rn(b3, rnper);
-            t1 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(t1, a0), a1), a2), a3);
-            t2 = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(t2, __dmul_rn(a0, a0)), __dmul_rn(a1, a1)), __dmul_rn(a2, a2)), __dmul_rn(a3, a3));
-        }
-        for (; j < nb; ++j) {
-            double bsum = 0.;
-            const i64 o = (i64)j*nper;
-            for (i64 i = 0; i < nper; ++i) { bsum = __dadd_rn(bsum, ld(o + i)); }
-            const double av = __dmul_rn(bsum, rnper);
-            t1 = __dadd_rn(t1, av);
-            t2 = __dadd_rn(t2, __dmul_rn(av, av));
-        }
-        s1[a] = t1;
-        s2[a] = t2;
+    for (int nb = 6; nb <= 50;) {
+        const int nb_hi = fc_group_end(n, nb);
+        fc_exact_group(n, ld, nb, nb_hi, [&](int a, double t1, double t2) { s1[a] = t1; s2[a] = t2; });
+        nb = nb_hi + 1;
     }
 }
 
@@ -624,6 +651,38 @@ __global__ void __launch_bounds__(32) fcblocker_smem_kernel(const double * __res
     fc_finish(s1, s2, nobs_is_one, wavg[col], werr[col]);
 }
 
+// The same with the partition groups of a chain spread over NW warps (the 100-sample chunks of the decorrelation loop: 0.8 ms per iteration
+// at 262144 chains when one thread per chain made the reference's 45 passes): every warp of the block handles some groups of the same 32
+// chains from the shared tile and warp 0 runs the plateau search. Every block sum is still accumulated in the reference's order.
+template <int NW>
+__global__ void __launch_bounds__(32*NW, 3) fcblocker_smem_par_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one,
+                                                                  double * __restrict__ wavg, double * __restrict__ werr)
+{
+    extern __shared__ double fc_tile[];
+    double * const st = fc_tile + n*32; // [90][32] partition statistics
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const i64 col = (i64)blockIdx.x*32 + lane;
+    const bool live = col < ncol;
+    for (i64 i = wq; i < n; i += NW) { fc_tile[i*32 + lane] = live ? __ldcs(data + i*ncol + col) : 0.; }
+    __syncthreads();
+    const double * src = fc_tile + lane;
+    int g = 0;
+    for (int nb = 6; nb <= 50; ++g) { // groups of partitions with a common block length, dealt round-robin to the warps (a group costs ~n adds whatever its size)
+        const int nb_hi = fc_group_end(n, nb);
+        if (g%NW == wq) {
+            fc_exact_group(n, [&](i64 i) { return src[i*32]; }, nb, nb_hi, [&](int a, double t1, double t2) {
+                st[(2*a)*32 + lane] = t1;
+                st[(2*a + 1)*32 + lane] = t2;
+            });
+        }
+        nb = nb_hi + 1;
+    }
+    __syncthreads();
+    if (wq == 0 && live) { // statistics stay in shared memory (per-thread arrays would be local memory, and the large carve-out leaves little L1)
+        fc_finish_inplace([&](int a) -> double & { return st[(2*a)*32 + lane]; }, [&](int a) -> double & { return st[(2*a + 1)*32 + lane]; },
+                          nobs_is_one, wavg[col], werr[col]);
+    }
+}
 
 // Event-driven FCBlocker for long series: ONE streaming pass with a single running sum per chain. The (position, partition)
 // pairs at which some partition completes a block are precomputed on the host and sorted by position (<= 1260 events);

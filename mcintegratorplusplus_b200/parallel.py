@@ -18,6 +18,9 @@ def shard(total_walkers, rank, world):
     return n, offset
 
 
+_staging = {}  # device index -> (pinned host tensor, device tensor): the messages are <= a few hundred bytes, allocating per call costs more than sending
+
+
 def allreduce_sum(buf, group=None):
     """In-place sum of a numpy float64 array over all ranks (no-op without an initialised process group)."""
     import torch
@@ -25,9 +28,20 @@ def allreduce_sum(buf, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return buf
     if dist.get_backend(group) == "nccl":
-        t = torch.from_numpy(np.ascontiguousarray(buf)).cuda()
-        dist.all_reduce(t, group=group)
-        buf[:] = t.cpu().numpy()
+        n = int(buf.size)
+        dev = torch.cuda.current_device()
+        st = _staging.get(dev)
+        if st is None or st[0].numel() < n:
+            cap = max(256, n)
+            st = (torch.empty(cap, dtype=torch.float64).pin_memory(), torch.empty(cap, dtype=torch.float64, device="cuda"))
+            _staging[dev] = st
+        host, devt = st
+        host[:n] = torch.from_numpy(np.ascontiguousarray(buf).reshape(-1))
+        devt[:n].copy_(host[:n], non_blocking=True)
+        dist.all_reduce(devt[:n], group=group)
+        host[:n].copy_(devt[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        buf.reshape(-1)[:] = host[:n].numpy()
     else:
         t = torch.from_numpy(np.ascontiguousarray(buf).copy())
         dist.all_reduce(t, group=group)
