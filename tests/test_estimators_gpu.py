@@ -78,6 +78,27 @@ def test_fcblocker_long_chains_time_split(mcig, oracle):
         assert np.array_equal(avg_c, avg) and np.array_equal(err_c, err)
 
 
+@pytest.mark.parametrize("n", [50, 51, 99, 100, 127, 198, 199, 346, 384, 385, 1000, 4096])
+def test_fcblocker_short_series_exact_paths(n, mcig, oracle):
+    """Short series (the 100- and 346-sample chunks of the decorrelation loop, src/MCIntegrator.cpp:193) run through the exact kernels: one pass per
+    distinct block length shared by a group of partitions, partition groups spread over the warps of a block for n <= 198, one thread per chain
+    up to 4096. Every block sum keeps the reference's order, so the oracle's values are reproduced to the last bits; 70 chains cross the
+    32-chain tiles of the shared-memory kernels."""
+    rng = np.random.default_rng(100 + n)
+    e = rng.normal(size=(n, 70))
+    x = np.empty_like(e)
+    x[0] = e[0]
+    for i in range(1, n):
+        x[i] = 0.7*x[i - 1] + e[i] + 0.5
+    avg_o, err_o = oracle.estimate(orc.EST_FCBLOCKER, x)
+    avg, err = mcig.estimate(orc.EST_FCBLOCKER, x)
+    assert np.allclose(avg, avg_o, rtol=1e-14, atol=0.), np.max(np.abs(avg - avg_o))
+    assert np.allclose(err, err_o, rtol=1e-13, atol=0.), np.max(np.abs(err/err_o - 1))
+    one_o = oracle.estimate(orc.EST_FCBLOCKER, x[:, 3].copy())
+    one = mcig.estimate(orc.EST_FCBLOCKER, x[:, 3].copy())  # the one-dimensional estimator divides where the multi-dimensional one multiplies (src/Estimators.cpp:69 vs :175)
+    assert np.allclose(one[0], one_o[0], rtol=1e-14, atol=0.) and np.allclose(one[1], one_o[1], rtol=1e-13, atol=0.)
+
+
 def test_constant_series_defined_error(mcig, oracle):
     """Constval-like data (test/main.cpp:82-88). An exactly representable constant has zero variance at every level: the
     reference then reads out of bounds; here and in the oracle err is defined as 0. A constant
