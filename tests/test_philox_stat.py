@@ -259,3 +259,34 @@ def test_stream_position_is_resumable_across_a_2_32_boundary(name, mcig):
         out.append((mci.getAcceptanceRate() if pieces == 1 else None, list(mci.getX())))
     assert all(o[1] == out[0][1] for o in out)
     assert all(o[0] == out[0][0] for o in out if o[0] is not None)
+
+
+def test_warp_specialised_kernel_reproduces_the_single_role_kernel():
+    """The experimental producer / consumer kernel (MCIG_WS=1: Philox blocks through a shared-memory ring with mbarrier hand-over) consumes the same
+    blocks in the same order: positions, acceptance and sums are bit-identical to the default kernel, also across a 2^32 boundary of the group
+    counter. The switch is read once per process, hence the subprocesses."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import json, sys
+sys.path.insert(0, %r)
+import mcintegratorplusplus_b200 as m
+out = []
+for start in (0, 5*2**32 - 3000):
+    mci = m.MCI(3); mci.setRngMode(0); mci.setSeed(99); mci.setNWalkers(256)
+    mci.addSamplingFunction(m.ThreeDimGaussianPDF()); mci.addObservable(m.XSquared(), 0, 1); mci.setMRT2Step(1.0)
+    mci.setDynamicScheduling(1); mci.setStreamPosition(start)
+    avg, err = mci.integrate(20000, False, False)
+    out.append([float(avg[0]).hex(), mci.getAcceptanceRate(), [float(v).hex() for v in mci.getX()], "mcig_walk_ws" in mci.kernelSource()])
+print(json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for ws in ("0", "1"):
+        env = dict(os.environ, MCIG_WS=ws)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert [o[3] for o in res[0]] == [False, False] and [o[3] for o in res[1]] == [True, True]
+    assert [o[:3] for o in res[0]] == [o[:3] for o in res[1]]
