@@ -1,0 +1,10 @@
+#!/bin/bash
+run() {
+  echo "== defs='$1'"
+  MCIG_JIT_DEFINES="$1" python tools/profile_walk.py 100000 65536 0 1
+  MCIG_JIT_DEFINES="$1" python tools/profile_walk.py 100000 303104 0 1
+}
+run ""
+run "MCIG_RK_REGS=1"
+run "MCIG_RK_REGS=1;MCIG_WALK_UNROLL_DYN=2"
+run "MCIG_RK_REGS=1;MCIG_WALK_UNROLL_DYN=4"
