@@ -54,6 +54,7 @@ enum {
     MCIG_PLUGIN_ELEMENTWISE = 2,    /* proto value k depends on x[k] only; updatedAcceptance touches protonew[changedIdx] only, by plain assignment /
                                      * reads (with HAS_UPDATE the new values of a selective update may live in registers, not in an array) */
     MCIG_PLUGIN_LOG_ACCEPTANCE = 4, /* functor provides logAcceptance(protoold, protonew) = log(acceptanceFunction) */
+    MCIG_PLUGIN_PROTO_ELEMENT = 16, /* sampling function (with ELEMENTWISE | HAS_UPDATE) provides protoElement(x_k) = proto value k */
     MCIG_PLUGIN_DEPENDENT = 8       /* observable: observableFunction(x, out, dep) with dep.proto(i) / dep.obs(k, j) (DependentObservableInterface) */
 };
 

@@ -16,6 +16,9 @@
 //       // optional (registration flag MCIG_PLUGIN_LOG_ACCEPTANCE): log of acceptanceFunction. When every sampling function
 //       // of an integrator provides it, production modes test u <= exp(sum of logs) with an FP32 pre-filter (accept_log).
 //       template <class PO, class PN> __device__ double logAcceptance(const PO & po, const PN & pn) const;
+//       // optional (flag MCIG_PLUGIN_PROTO_ELEMENT, with ELEMENTWISE | HAS_UPDATE): proto value k from x[k] alone; single-vector moves on shared- /
+//       // global-memory walkers then keep no proto-value array at all (old values are recomputed from the old coordinates)
+//       __device__ double protoElement(double xk) const;
 //       // with HAS_UPDATE as well: the selective counterpart (updates protonew like updatedAcceptance, returns the log)
 //       template <class W, class PO, class PN> __device__ double updatedLogAcceptance(const W & wlk, const PO & po, PN & pn) const;
 //   };
@@ -81,6 +84,7 @@ struct Gauss { // TestMCIFunctions.hpp:151-187 (nproto = ndim, selective update)
     static constexpr bool HAS_UPDATE = true;
     static constexpr bool ELEMENTWISE = true;
     const double * par;
+    MCIG_DEV double protoElement(double xk) const { return xk*xk; } // proto value k as a function of x[k] alone (MCIG_PLUGIN_PROTO_ELEMENT)
     template <class X, class P>
     MCIG_DEV void protoFunction(const X & in, P & pv) const
     {
@@ -164,6 +168,7 @@ struct ExpNDPDF { // TestMCIFunctions.hpp:217-256
     static constexpr bool HAS_UPDATE = true;
     static constexpr bool ELEMENTWISE = true;
     const double * par;
+    MCIG_DEV double protoElement(double xk) const { return fabs(xk); } // proto value k as a function of x[k] alone (MCIG_PLUGIN_PROTO_ELEMENT)
     template <class X, class P>
     MCIG_DEV void protoFunction(const X & in, P & pv) const
     {
