@@ -1,5 +1,5 @@
 #!/bin/bash
-# marginal accept path entered warp-uniformly (MCIG_ACCEPT_VOTE)
+# marginal accept path entered warp-uniformly (MCIG_ACCEPT_VOTE; the code was removed after this measurement, see accept_log in mcig_device.cuh)
 run() {
   echo "== defs='$1'"
   MCIG_JIT_DEFINES="$1" python tools/profile_walk.py 100000 65536 0 1
