@@ -119,3 +119,34 @@ def test_state_placement_follows_the_walker_size(mcig):
     assert "walk_kernel_gmem" in make(3, placement=2)
     with pytest.raises(McigError, match="shared memory"):
         make(512, placement=1)
+
+
+def test_all_move_footprint_and_unrolling_rules(mcig, monkeypatch):
+    """All-moves in state memory: an element-wise sampling function with protoElement needs no proto-value arrays (views over x and
+    the proposal, MS_MAIN_VPO; MCIG_ALL_VPO=0 keeps the arrays), which doubles the walkers per block; coordinate loops of 65 .. 256
+    coordinates are fully unrolled (the engine prepends MCIG_UNROLL_MAX 256 unless the experiment knob names it)."""
+    import re
+
+    def make(ndim, pdf=None):
+        mci = mcig.MCI(ndim)
+        mci.setRngMode(0)
+        mci.setNWalkers(4096)
+        mci.addSamplingFunction((pdf or mcig.ExpNDPDF)(ndim))
+        mci.addObservable(mcig.XND(ndim), 20, 1)
+        mci.prebuild()
+        return mci.kernelSource()
+
+    def block(src):
+        return int(re.search(r"BLOCK = (\d+)", src).group(1))
+
+    on = make(64)
+    assert "MS_MAIN_VPO = true" in on and "walk_kernel_smem" in on and "#define MCIG_UNROLL_MAX" not in on
+    monkeypatch.setenv("MCIG_ALL_VPO", "0")
+    off = make(64)
+    assert "MS_MAIN_VPO = false" in off and block(on) == 2*block(off)
+    monkeypatch.delenv("MCIG_ALL_VPO")
+    assert "MS_MAIN_VPO = false" in make(8)  # register-resident walkers keep their proto values in registers
+    assert "#define MCIG_UNROLL_MAX 256" in make(96)
+    assert "#define MCIG_UNROLL_MAX" not in make(320)
+    monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_UNROLL_MAX=16")
+    assert make(96).count("#define MCIG_UNROLL_MAX") == 1

@@ -117,6 +117,35 @@ def test_fp32_prefilter_never_changes_a_decision(case, mcig, monkeypatch):
         assert 0.2 < a[3] < 0.8
 
 
+ALL_VPO_SPECS = {
+    "all32_gauss": dict(ndim=32, seed=2031, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 20, 1)], nmc=4000, steps=(0.2,)),
+    "all24_expnd": dict(ndim=24, seed=2032, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 0, 1)], nmc=4000, steps=(0.6,)),
+    # (starts in the typical set, sum |x_j| ~ ndim: from the mode at the origin an all-move of 96 coordinates is accepted with p ~ 1e-6)
+    "all96_expnd_unrolled": dict(ndim=96, seed=2033, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=1000, steps=(0.15,),
+                                 x0=[1.0 if j % 2 == 0 else -1.0 for j in range(96)]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(ALL_VPO_SPECS))
+def test_all_move_proto_views_equal_proto_arrays(case, mcig, monkeypatch):
+    """All-moves in state memory read both sides of the acceptance test through ProtoViews over x and over the proposal when the
+    sampling function is element-wise with protoElement (no proto-value arrays: device/mcig_device.cuh walk_state, MS_VPO). The
+    recomputed proto values are the stored ones bit for bit, so per-walker results must not change (MCIG_ALL_VPO=0 keeps the arrays)."""
+    spec = ALL_VPO_SPECS[case]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MCIG_ALL_VPO", flag)
+        mci = build_mci(mcig, spec, nwalkers=1024, mode=0)
+        assert ("MS_MAIN_VPO = " + ("true" if flag == "1" else "false")) in mci.kernelSource()
+        avg, err = mci.integrate(spec["nmc"], False, False)
+        wavg, _ = mci.walkerResults()
+        res[flag] = (np.array(avg), np.array(err), wavg.copy(), mci.getAcceptanceRate(), np.array([mci.getX(walker=w) for w in (0, 511, 1023)]))
+    a, b = res["1"], res["0"]
+    assert np.array_equal(a[2], b[2]) and a[3] == b[3] and np.array_equal(a[4], b[4])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert 0.15 < a[3] < 0.85
+
+
 def test_two_sampling_functions_multiply(mcig):
     """SamplingFunctionContainer multiplies the acceptances of all pdfs (src/SamplingFunctionContainer.cpp:41-48):
     exp(-r^2) * exp(-r^2) = exp(-2 r^2)  =>  <x^2> = 1/4 per coordinate. Also exercises the log-acceptance sum of the pre-filter."""
