@@ -876,6 +876,13 @@ __global__ void transpose_kernel(const double * __restrict__ in, i64 W, i64 n, d
     }
 }
 
+// one walker's column of a stored series: out[r] = data[r*W + w], r < nrows (read-back of a chain: a strided 8-byte cudaMemcpy2D moves one row per
+// DMA descriptor, minutes for the 2^27 rows of a BASELINE configs[3] chain block)
+__global__ void gather_column_kernel(const double * __restrict__ data, i64 nrows, i64 W, i64 w, double * __restrict__ out)
+{
+    for (i64 r = (i64)blockIdx.x*blockDim.x + threadIdx.x; r < nrows; r += (i64)gridDim.x*blockDim.x) { out[r] = __ldcs(data + r*W + w); }
+}
+
 // ---------------------------------------------------------------------------------------------- issue-rate microbenchmarks
 template <int ILP>
 __global__ void dfma_peak_kernel(double * out, int iters, double a, double b)

@@ -84,6 +84,23 @@ RUNS = {
                      ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.5,), x0=_alt(16)),
     "ms_nosub8": dict(ndim=8, seed=5, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=4000, move_type=orc.MOVE_MULTISTEP, veclen=1, steps=(0.3,),
                       x0=_alt(8)),
+    # --- the shapes BASELINE configs[2] (C3) actually runs: ExpNDPDF / Gauss + XND with Block(20) at ndim 32 and 64
+    #     (benchmark/bench_throughput_ndim_single/main.cpp:26-50, src/MultiStepMove.cpp:6-47); every state placement is tested
+    "ms_sub32_b20": dict(ndim=32, seed=3201, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 20, 1)], nmc=2000, move_type=orc.MOVE_MULTISTEP, veclen=1,
+                         ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.5,), x0=_alt(32)),
+    "ms_sub64_b20": dict(ndim=64, seed=6401, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 20, 1)], nmc=1000, move_type=orc.MOVE_MULTISTEP, veclen=1,
+                         ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.5,), x0=_alt(64)),
+    "ms_nosub32_b20": dict(ndim=32, seed=3202, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=2000, move_type=orc.MOVE_MULTISTEP, veclen=1,
+                           steps=(0.05,), x0=_alt(32)),
+    "ms_nosub64_b20": dict(ndim=64, seed=6402, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=1000, move_type=orc.MOVE_MULTISTEP, veclen=1,
+                           steps=(0.03,), x0=_alt(64)),
+    "ndim_all32_b20": dict(ndim=32, seed=3203, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=20000, steps=(0.53,), x0=_alt(32)),
+    "ndim_all64_b20": dict(ndim=64, seed=6403, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=10000, steps=(0.375,), x0=_alt(64)),
+    "ndim_gauss_all32": dict(ndim=32, seed=3204, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1), (orc.OBS_XND, 0, 1)], nmc=16384, steps=(0.3,), x0=_alt(32)),
+    "ndim_vec32_b20": dict(ndim=32, seed=3205, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,),
+                           x0=_alt(32)),
+    "ndim_vec64_b20": dict(ndim=64, seed=6405, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,),
+                           x0=_alt(64)),
     # --- Gaussian proposals (SRRDType::Gaussian: std::normal_distribution, polar method with a cached value)
     "gauss_all": dict(ndim=3, seed=99, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 16, 1)], nmc=16384, srrd=orc.SRRD_GAUSSIAN, steps=(0.6,)),
     "gauss_all_auto": dict(ndim=3, seed=98, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=8192, srrd=orc.SRRD_GAUSSIAN, x0=(2., -2., 1.),
@@ -138,6 +155,10 @@ def in_oracle(name):
 
 
 # configurations whose step callback sums are pinned by the reference (oracle/ref_harness.cpp: mciref_run_callback)
+# the C3 shapes whose kernels are footprint- / register-limited: replayed on every state placement (tests/test_walk_parity.py)
+C3_SHAPES = ["ms_sub32_b20", "ms_sub64_b20", "ms_nosub32_b20", "ms_nosub64_b20", "ndim_all32_b20", "ndim_all64_b20", "ndim_gauss_all32",
+             "ndim_vec32_b20", "ndim_vec64_b20"]
+
 CALLBACK_RUNS = ["c1_simple_short", "vec_exp4", "ms_sub16", "auto_default", "ut2_irange", "nopdf_box", "gauss_vec6_v3"]
 
 

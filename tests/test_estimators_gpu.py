@@ -118,3 +118,25 @@ def test_estimator_argument_errors(mcig):
         mcig.estimate(orc.EST_FCBLOCKER, np.arange(40.))
     with pytest.raises(McigError, match="larger than 1"):
         mcig.estimate(orc.EST_UNCORRELATED, np.arange(1.))
+
+
+def test_c4_full_accumulator_mjblocker_through_the_walk(mcig, oracle):
+    """BASELINE configs[3] shape through the walk itself (not host data): FullAccumulator + MJBlocker on the 3-D Gaussian / x^2 integrand,
+    128 chains x 2^22 stored samples (4.3 GB staged in HBM by the walk kernel). Sampled chains are pulled back and re-estimated by the
+    oracle's 13-pass MJBlocker (src/MJBlocker.cpp:127-154): mean to 1e-12, error to 1e-9; the combination is src/MPIMCI.cpp:85-92."""
+    W, k = 128, 22
+    spec = dict(ndim=3, seed=2027, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_MJBLOCKER)], nmc=1 << k, steps=(1.0,))
+    from prod import build_mci
+    mci = build_mci(mcig, spec, nwalkers=W, mode=0)
+    avg, err = mci.integrate(1 << k, False, False)
+    wavg, werr = mci.walkerResults()
+    for w in (0, 77, W - 1):
+        x = mci.obsData(0, walker=w, nobs=1)[:, 0]
+        assert x.shape == (1 << k,)
+        a, e = oracle.estimate(orc.EST_MJBLOCKER, x)
+        assert wavg[0, w] == pytest.approx(a[0], rel=1e-12)
+        assert werr[0, w] == pytest.approx(e[0], rel=1e-9)
+        assert e[0] > 0
+    assert avg[0] == pytest.approx(wavg[0].sum()/W, rel=1e-13)
+    assert err[0] == pytest.approx(np.sqrt((werr[0]**2).sum())/W, rel=1e-12)
+    assert abs(avg[0] - 0.5) < 4*err[0]

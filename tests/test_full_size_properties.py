@@ -81,3 +81,29 @@ def test_full_accumulator_round_trip_at_scale(mcig):
         assert full.shape == (1 << 14,) and blocks.shape == (1 << 10,)
         ref_blocks = np.array([np.sum(full[16*i:16*(i + 1)]) for i in range(1 << 10)])*(1./16)
         assert np.allclose(blocks, ref_blocks, rtol=1e-15, atol=0)
+
+
+def test_c4_full_size_chain_blocks_through_the_walk(mcig, oracle):
+    """BASELINE configs[3] at its stated size: FullAccumulator + MJBlocker with n = 2^27 stored samples per chain block
+    (benchmark/bench_estimators/main.cpp:31-50 rounds 1e8 up to the power of two src/MJBlocker.cpp:28-30 demands), staged in HBM by
+    the walk kernel for as many chains as fit (128 chains = 137 GB; fewer on a box with less free memory, never below 16).
+    One chain block is read back (1 GiB) and re-estimated by the oracle's own MJBlocker: mean 1e-12, error 1e-9."""
+    import torch
+    k = 27
+    free, _ = torch.cuda.mem_get_info()
+    W = 128
+    while W > 16 and W*(8 << k)*1.06 + (2 << 30) > free:
+        W //= 2
+    if W*(8 << k)*1.06 + (2 << 30) > free:
+        pytest.skip("not enough free HBM for 16 chain blocks of 2^27 samples")
+    spec = dict(ndim=3, seed=2028, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_MJBLOCKER)], nmc=1 << k, steps=(1.0,))
+    mci = build_mci(mcig, spec, nwalkers=W, mode=0)
+    avg, err = mci.integrate(1 << k, False, False)
+    wavg, werr = mci.walkerResults()
+    w = W - 3
+    x = mci.obsData(0, walker=w, nobs=1)[:, 0]
+    assert x.shape == (1 << k,)
+    a, e = oracle.estimate(orc.EST_MJBLOCKER, x)
+    assert wavg[0, w] == pytest.approx(a[0], rel=1e-12) and werr[0, w] == pytest.approx(e[0], rel=1e-9)
+    assert abs(avg[0] - 0.5) < 4*err[0] and err[0] < 2e-5*np.sqrt(128/W)
+    del mci

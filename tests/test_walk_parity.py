@@ -64,6 +64,45 @@ def test_register_and_smem_paths_agree(name, placement, mcig, oracle):
     assert _close(avg, ref["avg"], AVG_RTOL) and _close(err, ref["err"], ERR_RTOL, atol=1e-18)
 
 
+@pytest.mark.parametrize("placement", [0, 1, 2])
+@pytest.mark.parametrize("name", configs.C3_SHAPES)
+def test_c3_shapes_replay_on_every_placement(name, placement, mcig, oracle, golden_runs):
+    """The shapes BASELINE configs[2] runs (ExpNDPDF / Gauss + XND, Block(20), ndim 32 and 64: MultiStepMove with and without sub-pdf,
+    all-move, single-index vec move) are the register- / footprint-limited kernels where a spill or unroll bug would hide: every
+    placement (registers with local-memory indexing, shared memory, global memory) replays the reference bit for bit.
+    Reference: src/MultiStepMove.cpp:6-47, benchmark/bench_throughput_ndim_single/main.cpp:26-50."""
+    spec = configs.RUNS[name]
+    g = golden_runs[name]
+    ref = oracle.run(configs.make(name))
+    assert ref["avg"] == fromhex(g["avg"]) and ref["x_final"] == fromhex(g["x_final"])
+    mci = build_mci(mcig, spec, placement=placement)
+    avg, err = mci.integrate(spec["nmc"], False, False)
+    assert round(mci.getAcceptanceRate()*spec["nmc"]) == g["n_acc"], "accept count differs"
+    assert list(mci.getX()) == ref["x_final"], "final position not bit-exact"
+    assert _close(avg, ref["avg"], AVG_RTOL), np.max(np.abs(avg - np.array(ref["avg"])))
+    assert _close(err, ref["err"], ERR_RTOL, atol=1e-18)
+
+
+@pytest.mark.parametrize("name", configs.C3_SHAPES)
+def test_c3_shapes_philox_placements_agree(name, mcig):
+    """Production (Philox) kernels of the same shapes: the shared- and global-memory placements run the same code over different views
+    and must agree bit for bit; the register placement may contract products differently, so it must reproduce every accept decision
+    (positions and acceptance count bit-identical) and the averages to rounding."""
+    spec = configs.RUNS[name]
+    n = min(spec["nmc"], 2000)
+    out = []
+    for placement in (0, 1, 2):
+        mci = build_mci(mcig, spec, nwalkers=160, mode=0, placement=placement)
+        mci.setLazyAccumulation(0)
+        avg, err = mci.integrate(n, False, False)
+        out.append((avg.copy(), err.copy(), mci.getAcceptanceRate(), [list(mci.getX(walker=w)) for w in (0, 77, 159)]))
+    assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1], out[2][1]) and out[1][2:] == out[2][2:]
+    assert out[0][2] == out[1][2]
+    assert np.allclose(out[0][3], out[1][3], rtol=1e-12, atol=1e-14)
+    scale = max(1.0, float(np.max(np.abs(out[1][0]))))
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-12*scale
+
+
 def test_accept_sequence_and_trajectory_bit_exact(mcig, oracle):
     """Every step: positions from a Full XND accumulator vs the trajectory implied by the oracle's draws + accept bits."""
     nmc = 20000
