@@ -5,20 +5,26 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...     # the reference's own CPU implementation on the host cores
 
-Workload ("bench_throughput_3G" of BASELINE.json configs[1], pinned in SURVEY.md §8(d) C2): ThreeDimGaussianPDF + XSquared,
+Headline workload ("bench_throughput_3G" of BASELINE.json configs[1], pinned in SURVEY.md §8(d) C2): ThreeDimGaussianPDF + XSquared,
 uniform all-move step 1.0, SimpleAccumulator, 65536 walkers per GPU x 1e5 Metropolis steps. One bench "step" = one
-mci.integrate(1e5, avg, err, false, false) over all walkers of the rank (6.5536e9 samples per GPU). Weak scaling: the
-walkers per GPU are fixed, global walker ids rank*65536.., one all-reduce of [sum avg | sum err^2] per integrate.
+mci.integrate(1e5, avg, err, false, false) over all walkers of the rank (6.5536e9 samples per GPU). Weak scaling: the walkers per GPU
+are fixed, global walker ids rank*65536.., one all-reduce of [sum avg | sum err^2] per integrate — issued by the library itself as an
+ncclAllReduce on the engine's stream (include/mcig.h: mcig_comm_*, mcig_attach_comm); torch.distributed only transports the NCCL id,
+the barriers and the max-over-ranks of the timings.
 
 value  : samples/s, inputs resident in HBM, device time (CUDA events on the engine's stream around the whole integrate call),
          max over ranks.
 e2e    : the same metric through the public C-ABI call sequence with HOST buffers — set walker positions from host memory
          (H2D), integrate, read avg/err/acceptance back (D2H) — wall clock around the calls, max over ranks.
 roofline: FP64 issue rate. achieved = 34 algorithmic FP64 instructions per Metropolis step x steps / walk-kernel
-         time; peak = DFMA/s measured live on the same GPU by the library's microbenchmark (MEASURED_PEAKS.json has no FP64 figure).
+         time; peak = DFMA/s measured live on the same GPU (MEASURED_PEAKS.json has no FP64 figure); the nominal peak
+         (64 FP64 lanes x 148 SMs x max SM clock) and the fraction against it are printed next to it.
+secondary: the other BASELINE.json configs, measured OUTSIDE the timed headline region, each with its own roofline and CPU baseline:
+         C3 (configs[2]: dimension sweep, vec / all / MultiStepMove, Block(20)), C4 (configs[3]: Full + MJBlocker, HBM-bound),
+         C5 (configs[4]: mixed observables with automatic calibration + decorrelation; sharded over the ranks under torchrun) and the
+         strong-scaling variant of the headline (65536 walkers in total).
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -36,6 +42,22 @@ FLOP_PER_STEP = 53
 WALK_DRAM_BYTES_PER_LAUNCH = 1586176  # ncu dram__bytes_read.sum (+ 0 written) of one mcig_walk_dyn launch, profiles/r01_walk_r1f_dyn_ncu_raw.csv
 METRIC = "metropolis_samples_per_sec"
 WORKLOAD = "bench_throughput_3G: ThreeDimGaussianPDF ndim=3 + XSquared, uniform all-move step 1.0, SimpleAccumulator, 65536 walkers/GPU x 1e5 steps"
+FP64_LANES_PER_SM, N_SM = 64, 148
+REF_NMC = 15000000  # Metropolis steps per chain of one reference-arm bench step / of the cpu_baseline sample (~1.5 s per chain)
+
+
+def bench_config(world):
+    return {"workload": WORKLOAD, "rng": "Philox4x32-10, 32-bit uniforms", "walkers_per_gpu": WALKERS_PER_GPU, "nmc": NMC,
+            "l2": "no HBM inputs to cache: walker state lives in registers; 1.5 MB of positions read once per step",
+            "parallelism": "walkers sharded over %d GPU(s), 1 all-reduce of 2 doubles per integrate" % world}
+
+
+def hbm_peak():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -57,9 +79,6 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line))
-
-    def mark(self):
-        return time.perf_counter()
 
     def stop(self):
         if self.proc is not None:
@@ -89,67 +108,362 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None}
 
 
-def make_mci(m, rank, world):
-    mci = m.MCI(3, device=int(os.environ.get("LOCAL_RANK", 0)))
-    mci.setRngMode(m.RngMode.Philox32)
-    mci.setSeed(1337)
-    mci.setNWalkers(WALKERS_PER_GPU, global_offset=rank*WALKERS_PER_GPU, total=world*WALKERS_PER_GPU)
-    mci.addSamplingFunction(m.ThreeDimGaussianPDF())
-    mci.addObservable(m.XSquared(), 0, 1)  # blocksize 0: SimpleAccumulator + Noop estimator
-    mci.setMRT2Step(1.0)  # acceptance ~0.5 (benchmark/bench_integrate_mixed/main.cpp:44)
-    return mci
+# ---------------------------------------------------------------------------------------------------------------- reference on the host cores
+_WORKER = r"""
+import sys, json, time
+sys.path.insert(0, %(orc_dir)r)
+import numpy as np
+import orc
+e = orc.Engine(%(path)r, %(prefix)r)
+cache = {}
+print("ready", flush=True)
+for line in sys.stdin:
+    t = json.loads(line)
+    if t.get("quit"):
+        break
+    if t["kind"] == "run":
+        kw = dict(t["kw"])
+        kw["obs"] = [tuple(o) for o in kw["obs"]]
+        kw["seed"] = kw["seed"] + t["index"]
+        cfg = orc.make_config(kw.pop("ndim"), kw.pop("seed"), kw.pop("pdf_id"), kw.pop("obs"), t["nmc"], **kw)
+        while time.time() < t["t_start"]:
+            pass
+        t0 = time.time()
+        r = e.run(cfg)
+        t1 = time.time()
+        print(json.dumps({"t0": t0, "t1": t1, "avg0": (r["avg"][0] if r["avg"] else 0.0), "acc": r["acc_rate"]}), flush=True)
+    else:  # MJBlocker on an AR(1) series of n samples (benchmark/bench_estimators)
+        n = t["n"]
+        if n not in cache:
+            rng = np.random.default_rng(7 + t["index"])
+            x = rng.normal(size=n)
+            for i in range(1, n):
+                x[i] += 0.5*x[i - 1]
+            cache = {n: x}
+        x = cache[n]
+        while time.time() < t["t_start"]:
+            pass
+        t0 = time.time()
+        a, er = e.estimate(orc.EST_MJBLOCKER, x)
+        t1 = time.time()
+        print(json.dumps({"t0": t0, "t1": t1, "avg0": float(a[0]), "acc": float(er[0])}), flush=True)
+"""
 
 
-def cpu_reference_run(nmc, nproc):
-    """The reference's CPU implementation of the same path on the host cores: P independent chains (one per core, the
-    reference's MPI model, src/MPIMCI.cpp:83), each nmc steps. Uses oracle/_ref (the unmodified reference) when it was
-    built, else the C port. Returns (samples/s, kind, wall seconds)."""
+class CpuPool:
+    """The reference's CPU implementation on ALL host cores: P persistent worker processes, each one independent chain (one `MCI` per
+    core is the reference's MPI model, src/MPIMCI.cpp:83). The unmodified reference compiled with its own tuning flags
+    (oracle/_ref/libmci_ref_v4|v3.so, see oracle/Makefile) when it was built, else the C restatement. A task starts on every worker at
+    the same wall-clock instant and is timed INSIDE the workers: wall = last finish - common start, no process start-up or teardown."""
+
+    def __init__(self, nproc=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        self.orc = orc
+        self.nproc = nproc or os.cpu_count() or 1
+        if orc.have_ref():
+            path, self.flags = orc.ref_timing_path()
+            self.kind, prefix = "reference", "mciref"
+        else:
+            if not os.path.exists(orc.ORACLE_PATH):
+                subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
+            path, self.flags, self.kind, prefix = orc.ORACLE_PATH, "gcc -O3 -ffp-contract=off (C restatement)", "port", "mcio"
+        code = _WORKER % {"orc_dir": os.path.join(ROOT, "oracle"), "path": path, "prefix": prefix}
+        self.procs = [subprocess.Popen([sys.executable, "-c", code], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True) for _ in range(self.nproc)]
+        for p in self.procs:
+            assert p.stdout.readline().strip() == "ready"
+
+    def _go(self, task):
+        t_start = time.time() + 0.05
+        for i, p in enumerate(self.procs):
+            p.stdin.write(json.dumps(dict(task, index=i, t_start=t_start)) + "\n")
+            p.stdin.flush()
+        outs = [json.loads(p.stdout.readline()) for p in self.procs]
+        return max(o["t1"] for o in outs) - t_start, outs
+
+    def run(self, kw, nmc):
+        """P chains x nmc Metropolis steps of the configuration `kw` (oracle/orc.py:make_config keywords). Returns (steps/s, wall s, outs)."""
+        wall, outs = self._go({"kind": "run", "kw": kw, "nmc": int(nmc)})
+        return self.nproc*nmc/wall, wall, outs
+
+    def mjblocker(self, n):
+        """P independent series of n samples through the reference's MJBlocker. Returns (GB/s of series read once, wall s)."""
+        self._go({"kind": "est", "n": int(n)})  # first call generates the data
+        wall, outs = self._go({"kind": "est", "n": int(n)})
+        return self.nproc*8.0*n/wall/1e9, wall
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.write('{"quit": 1}\n')
+                p.stdin.flush()
+                p.wait(timeout=5)
+            except Exception:
+                p.kill()
+
+
+def _orc_ids():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
-    kind = "reference" if orc.have_ref() else "port"
-    if kind == "port" and not os.path.exists(orc.ORACLE_PATH):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
-    code = (
-        "import sys,time; sys.path.insert(0,%r); import orc\n"
-        "e = orc.ref() if %r=='reference' else orc.oracle()\n"
-        "c = orc.make_config(3, int(sys.argv[1]), orc.PDF_GAUSS3D, [(orc.OBS_XSQUARED,0,1)], int(sys.argv[2]), steps=(1.0,))\n"
-        "sys.stdin.readline(); t=time.perf_counter(); r=e.run(c); print(time.perf_counter()-t, r['avg'][0])\n"
-    ) % (os.path.join(ROOT, "oracle"), kind)
-    procs = [subprocess.Popen([sys.executable, "-c", code, str(1000 + p), str(nmc)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
-             for p in range(nproc)]
-    time.sleep(1.5)  # let every interpreter load the library before the start signal
-    t0 = time.perf_counter()
-    for p in procs:
-        p.stdin.write("go\n")
-        p.stdin.flush()
-    outs = [p.communicate()[0] for p in procs]
-    wall = time.perf_counter() - t0
-    avgs = [float(o.split()[1]) for o in outs]
-    assert all(0.3 < a < 0.7 for a in avgs), avgs
-    return nproc*nmc/wall, kind, wall
+    return orc
+
+
+def c2_kw():
+    orc = _orc_ids()
+    return dict(ndim=3, seed=1000, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 0, 1)], steps=(1.0,))
 
 
 def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the headline workload, all host cores, one chain per core,
+    REF_NMC steps per chain per bench step, timed inside the worker processes."""
     if rank != 0:
         return
-    nproc = os.cpu_count() or 1
-    nmc = 4000000  # bounded sample: ~0.5 s per chain per step
+    pool = CpuPool()
+    kw = c2_kw()
     for _ in range(args.warmup):
-        cpu_reference_run(max(100000, nmc//10), nproc)
-    t = []
-    kind = "port"
+        pool.run(kw, REF_NMC//10)
+    walls = []
     for _ in range(args.steps):
-        v, kind, wall = cpu_reference_run(nmc, nproc)
-        t.append(wall)
-    total = sum(t)
-    value = args.steps*nproc*nmc/total
+        v, wall, outs = pool.run(kw, REF_NMC)
+        assert all(0.3 < o["avg0"] < 0.7 for o in outs), outs
+        walls.append(wall)
+    pool.close()
+    total = sum(walls)
+    value = args.steps*pool.nproc*REF_NMC/total
+    sample = "%d independent chains (one per host core) x %.1e Metropolis steps of the same integrand per bench step; %s" % (pool.nproc, REF_NMC, pool.flags)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3*total/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": "%d host processes x %d steps per bench step" % (nproc, nmc)},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": nproc, "kind": kind,
-                             "sample": "%d independent chains (one per core) x %d Metropolis steps of the same integrand" % (nproc, nmc)},
+            "dtype": "f64", "data": "synthetic", "config": bench_config(world),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": pool.nproc, "kind": pool.kind, "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arms
+def make_mci(m, rank, world, walkers=WALKERS_PER_GPU, device=None):
+    mci = m.MCI(3, device=int(os.environ.get("LOCAL_RANK", 0)) if device is None else device)
+    mci.setRngMode(m.RngMode.Philox32)
+    mci.setSeed(1337)
+    mci.setNWalkers(walkers, global_offset=rank*walkers, total=world*walkers)
+    mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+    mci.addObservable(m.XSquared(), 0, 1)  # blocksize 0: SimpleAccumulator + Noop estimator
+    mci.setMRT2Step(1.0)  # acceptance ~0.5 (benchmark/bench_integrate_mixed/main.cpp:44)
+    if world > 1:
+        mci.attachComm()
+    return mci
+
+
+C3_NDIMS = (1, 2, 4, 8, 16, 32, 64)
+
+
+def c3_mci(m, move, nd, W, local):
+    """BASELINE configs[2]: ExpNDPDF + XND with BlockAccumulator(20); `vec` is the reference's own single-particle sweep
+    (benchmark/bench_throughput_ndim_single/main.cpp:26-50), `all` its all-move twin, `multistep` MultiStepMove(ndim sub-steps of a
+    single-index uniform move) with main pdf Gauss and sub-pdf ExpNDPDF as in test/ut5/main.cpp:113-127."""
+    mci = m.MCI(nd, device=local)
+    mci.setRngMode(0)
+    mci.setSeed(1337)
+    mci.setNWalkers(W)
+    if move == "vec":
+        mci.setTrialMove(m.MoveType.Vec)
+    elif move == "multistep":
+        mci.setTrialMove(m.MoveType.MultiStep, 1, sub_pdfs=[m.ExpNDPDF(nd)] if nd > 1 else [])
+    else:
+        mci.setTrialMove(m.MoveType.All)
+    mci.setX([0.1 if j % 2 == 0 else -0.05 for j in range(nd)])
+    mci.setMRT2Step(3.0 if move == "vec" else (0.5 if move == "multistep" else 3.0/nd**0.5))
+    mci.addSamplingFunction(m.ExpNDPDF(nd) if move != "multistep" else m.Gauss(nd))
+    mci.addObservable(m.XND(nd), 20, 1)  # BlockAccumulator(20) + Uncorrelated
+    return mci
+
+
+def c3_kw(move, nd):
+    orc = _orc_ids()
+    x0 = [0.1 if j % 2 == 0 else -0.05 for j in range(nd)]
+    if move == "vec":
+        return dict(ndim=nd, seed=2000, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,), x0=x0)
+    if move == "all":
+        return dict(ndim=nd, seed=2000, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], steps=(3.0/nd**0.5,), x0=x0)
+    return dict(ndim=nd, seed=2000, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 20, 1)], move_type=orc.MOVE_MULTISTEP, veclen=1,
+                ms_sub_pdf_id=orc.PDF_EXPND if nd > 1 else orc.PDF_NONE, steps=(0.5,), x0=x0)
+
+
+def c3_work(move, nd):
+    """Algorithmic FP64-pipe instructions and Philox4x32 blocks per Metropolis step (SURVEY.md §8d formulas)."""
+    if move == "vec":    # 2 uniforms + proposal 2 + proto delta 1 + exp 17 + compare 1 = 23, + ndim accumulate; 3 draws = 1 block
+        return 23 + nd, 1
+    if move == "all":    # (ndim+1) uniforms + 2 ndim proposal + 2 ndim proto sums + 1 + exp 17 + compare 1 + ndim accumulate
+        return (nd + 1) + 2*nd + 2*nd + 1 + 17 + 1 + nd, (nd + 1 + 3)//4
+    return 28*nd + 64, nd + 1  # MultiStepMove: 23 per sub-step + outer test, one block per sub-step + one for the outer accept draw
+
+
+def secondary_c3(m, local, peaks, philox_peak, pool):
+    out = {}
+    W = 65536
+    for move in ("vec", "all", "multistep"):
+        rows = []
+        for nd in C3_NDIMS:
+            nmc = {"vec": 8000, "all": 4000 if nd <= 16 else 2000}.get(move, max(200, 8000//(2*nd)//20*20))
+            mci = c3_mci(m, move, nd, W, local)
+            mci.integrate(max(200, nmc//10//20*20), False, False)
+            best = None
+            for _ in range(2):
+                avg, err = mci.integrate(nmc, False, False)
+                t = mci.timings()
+                best = t if best is None or t["walk_ms"] < best["walk_ms"] else best
+            sps = W*nmc/(best["walk_ms"]*1e-3)
+            instr, blocks = c3_work(move, nd)
+            row = {"ndim": nd, "steps_per_s": sps, "walk_ms": best["walk_ms"], "estim_ms": best["estim_ms"], "nmc": nmc, "acceptance": mci.getAcceptanceRate(),
+                   "roofline": {"bound": "fp64_issue", "fp64_instr_per_step": instr, "achieved": instr*sps/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s",
+                                "frac": instr*sps/peaks[0], "philox_blocks_per_step": blocks, "rng_frac": blocks*sps/philox_peak}}
+            if pool is not None:
+                nmc_cpu = max(2000, int({"vec": 3e6/(1 + nd/6.0), "all": 3e6/(1 + nd/1.5)}.get(move, 3e6/(1 + 6.0*nd)))//20*20)
+                v, wall, _ = pool.run(c3_kw(move, nd), nmc_cpu)
+                row["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": pool.nproc, "kind": pool.kind,
+                                       "sample": "%d chains x %d steps, %.2f s" % (pool.nproc, nmc_cpu, wall)}
+            rows.append(row)
+            del mci
+        out[move] = rows
+    return {"workload": "BASELINE configs[2]: ExpNDPDF/Gauss + XND, BlockAccumulator(20), 65536 walkers, ndim 1..64; moves: vec (single index, "
+                        "the reference's bench_throughput_ndim_single), all, multistep (MultiStepMove, ndim sub-steps, sub-pdf ExpNDPDF)",
+            "unit": "Metropolis steps/s (walk kernel, CUDA events)", **out}
+
+
+def secondary_c4(m, local, pool):
+    """BASELINE configs[3]: FullAccumulator + MJBlocker with device-side HBM staging. (a) 65536 chains x 2^14 samples (8.6 GB staged by the
+    walk, one streaming read by the estimator); (b) the same integrand at 65536 chains x 2^20 = 550 GB of series, which does not fit HBM:
+    staged and folded chunk by chunk (chunked Full staging)."""
+    peak, src = hbm_peak()
+    W, npow = 65536, 14
+    nmc = 1 << npow
+    out = {"workload": "BASELINE configs[3]: ThreeDimGaussianPDF + XSquared, FullAccumulator + MJBlocker, device-side HBM staging"}
+    rows = []
+    for label, est in (("MJBlocker", m.EstimatorType.MJBlocker), ("FCBlocker", m.EstimatorType.FCBlocker)):
+        mci = m.MCI(3, device=local)
+        mci.setRngMode(0)
+        mci.setSeed(1337)
+        mci.setNWalkers(W)
+        mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+        mci.addObservable(m.XSquared(), 1, 1, False, est)
+        mci.setMRT2Step(1.0)
+        mci.integrate(nmc, False, False)
+        ts = []
+        for _ in range(5):
+            avg, err = mci.integrate(nmc, False, False)
+            ts.append(mci.timings())
+        e_ms = min(q["estim_ms"] for q in ts)
+        w_ms = min(q["walk_ms"] for q in ts)
+        nbytes = 8.0*nmc*W
+        rows.append({"estimator": label, "walkers": W, "n_per_chain": nmc, "series_GB": nbytes/1e9, "walk_ms": w_ms, "estim_ms": e_ms,
+                     "walk_steps_per_s": W*nmc/(w_ms*1e-3), "walk_store_GBps": nbytes/(w_ms*1e-3)/1e9, "avg": float(avg[0]), "err": float(err[0]),
+                     "roofline": {"bound": "hbm", "achieved": nbytes/(e_ms*1e-3)/1e9, "peak": peak, "unit": "GB/s", "frac": nbytes/(e_ms*1e-3)/1e9/peak,
+                                  "peak_source": src, "algorithmic_bytes": "8 B per stored sample: one read of the series (the mean comes from the walk's running sum)"}})
+        del mci
+    out["in_hbm"] = rows
+    # (b) series larger than HBM
+    try:
+        W2, npow2 = 65536, 20
+        mci = m.MCI(3, device=local)
+        mci.setRngMode(0)
+        mci.setSeed(1337)
+        mci.setNWalkers(W2)
+        mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+        mci.addObservable(m.XSquared(), 1, 1, False, m.EstimatorType.MJBlocker)
+        mci.setMRT2Step(1.0)
+        mci.integrate(1 << npow2, False, False)
+        t0 = time.perf_counter()
+        avg, err = mci.integrate(1 << npow2, False, False)
+        wall = time.perf_counter() - t0
+        t = mci.timings()
+        nbytes = 8.0*(1 << npow2)*W2
+        out["beyond_hbm"] = {"walkers": W2, "n_per_chain": 1 << npow2, "series_GB": nbytes/1e9, "total_ms": t["total_ms"], "wall_ms": 1e3*wall,
+                             "samples_per_s": W2*(1 << npow2)/(t["total_ms"]*1e-3), "staged_GBps_write_plus_read": 2*nbytes/(t["total_ms"]*1e-3)/1e9,
+                             "avg": float(avg[0]), "err": float(err[0]),
+                             "roofline": {"bound": "hbm", "achieved": 2*nbytes/(t["total_ms"]*1e-3)/1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": 2*nbytes/(t["total_ms"]*1e-3)/1e9/peak, "peak_source": src,
+                                          "algorithmic_bytes": "16 B per stored sample: written once by the walk, read once by the estimator (SURVEY.md §8d)"}}
+        del mci
+    except Exception as ex:  # reported, not hidden: the in-HBM rows above stand on their own
+        out["beyond_hbm"] = {"error": str(ex)[:300]}
+    if pool is not None:
+        gbs, wall = pool.mjblocker(1 << 21)
+        out["cpu_baseline"] = {"value": gbs, "unit": "GB/s of series (read once)", "cores": pool.nproc, "kind": pool.kind,
+                               "sample": "%d series x 2^21 samples through the reference's MJBlocker (src/MJBlocker.cpp), %.2f s" % (pool.nproc, wall)}
+    return out
+
+
+def c5_mci(m, local, W, rank=0, world=1):
+    mci = m.MCI(3, device=local)
+    mci.setRngMode(0)
+    mci.setSeed(5649871)
+    mci.setNWalkers(W, global_offset=rank*W, total=world*W)
+    mci.addSamplingFunction(m.ThreeDimGaussianPDF())
+    mci.addObservable(m.XND(3), 0, 1)        # Simple
+    mci.addObservable(m.XSquared(), 1, 5)    # Full, nskip 5, Correlated
+    mci.addObservable(m.XYZSquared(), 5, 2)  # Block(5), nskip 2, Uncorrelated
+    mci.setMRT2Step(1.0)
+    if world > 1:
+        mci.attachComm()
+    return mci
+
+
+def secondary_c5(m, local, rank, world, peaks, pool, barrier, maxreduce):
+    """BASELINE configs[4]: bench_integrate_mixed (benchmark/bench_integrate_mixed/main.cpp:28-46) with automatic step calibration and
+    decorrelation, 65536 walkers per GPU sharded over the ranks; every all-reduce of the two control loops and the final one run inside
+    the library (NCCL on the engine's stream)."""
+    W, nmc = 65536, 100000
+    mci = c5_mci(m, local, W, rank, world)
+    for _ in range(2):  # the first automatic run loads the calibration / equilibration kernel variants
+        mci.setMRT2Step(1.0)
+        mci.integrate(nmc, True, True)
+    runs = []
+    for _ in range(3):
+        mci.setMRT2Step(1.0)
+        barrier()
+        avg, err = mci.integrate(nmc, True, True)
+        t = mci.timings()
+        t["total_ms"] = maxreduce(t["total_ms"])
+        runs.append((t, avg, err))
+    t, avg, err = min(runs, key=lambda q: q[0]["total_ms"])
+    sps = float(world)*W*nmc/(t["total_ms"]*1e-3)
+    instr = 34 + 3 + 2.0/5 + 6.0/2
+    out = {"workload": "BASELINE configs[4]: ThreeDimGaussianPDF; XND(3) Simple + XSquared Full nskip 5 (Correlated) + XYZSquared Block(5) nskip 2 (Uncorrelated), "
+                       "integrate(1e5, findMRT2Step=true, decorrelation=true), 65536 walkers per GPU",
+           "n_gpus": world, "samples_per_s": sps, "total_ms": t["total_ms"], "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "find_ms": t["find_ms"],
+           "decorr_ms": t["decorr_ms"], "launches": t["launches"], "calibration_iterations": mci.getCalibrationIterations(),
+           "decorrelation_chunks": mci.getDecorrelationChunks(), "step": mci.getMRT2Step(0), "acceptance": mci.getAcceptanceRate(),
+           "avg": [float(v) for v in avg], "err": [float(v) for v in err],
+           "roofline": {"bound": "fp64_issue", "fp64_instr_per_step": instr, "achieved": instr*sps/world/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s",
+                        "frac": instr*sps/world/peaks[0],
+                        "note": "34 (C2) + 3 (XND accumulate) + 2/5 (XSquared every 5th step) + 6/2 (XYZSquared every 2nd); whole integrate incl. both control loops and the estimators; "
+                                "HBM: 1.6 B/step written + read for the Full series, nothing for the Block(5) leg (one-pass estimator fused into the walk)"}}
+    if pool is not None and rank == 0:
+        orc = _orc_ids()
+        kw = dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_XSQUARED, 1, 5), (orc.OBS_XYZSQUARED, 5, 2)], steps=(1.0,),
+                  do_find=True, do_decorr=True)
+        v, wall, _ = pool.run(kw, 2000000)
+        out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": pool.nproc, "kind": pool.kind,
+                               "sample": "%d chains x 2e6 steps incl. calibration + decorrelation, %.2f s" % (pool.nproc, wall)}
+    del mci
+    return out
+
+
+def secondary_strong(m, local, rank, world, barrier, maxreduce):
+    """Fixed total work: 65536 walkers over N GPUs (thin grids: the dynamically scheduled kernel's case)."""
+    w = WALKERS_PER_GPU//world
+    mci = make_mci(m, rank, world, walkers=w, device=local)
+    for _ in range(3):
+        mci.integrate(NMC, False, False)
+    barrier()
+    ms = 0.0
+    reps = 5
+    for _ in range(reps):
+        mci.integrate(NMC, False, False)
+        ms += mci.timings()["total_ms"]
+    ms = maxreduce(ms)
+    del mci
+    return {"workload": "headline integrand, 65536 walkers in TOTAL over %d GPU(s) (%d per GPU) x 1e5 steps" % (world, w), "scaling": "strong", "n_gpus": world,
+            "samples_per_s": float(WALKERS_PER_GPU)*NMC*reps/(ms*1e-3), "ms_per_step": ms/reps}
 
 
 def main():
@@ -159,6 +473,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -169,7 +484,7 @@ def main():
     import numpy as np
     import torch
     import mcintegratorplusplus_b200 as m
-    from mcintegratorplusplus_b200 import _capi
+    from mcintegratorplusplus_b200 import _capi, parallel
     if _capi.lib().mcig_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device — the sampling path has no CPU fallback")
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -178,17 +493,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        parallel.init_comm(local)  # the library's own NCCL communicator (id broadcast through torch.distributed)
 
     mci = make_mci(m, rank, world)
-    if dist is not None:
-        red = torch.zeros(16, dtype=torch.float64, device="cuda")
-
-        def allreduce(buf):  # the single collective of the path: [sum avg | sum err^2] over NVLink (src/MPIMCI.cpp:85-87)
-            n = len(buf)
-            red[:n].copy_(torch.from_numpy(buf))
-            dist.all_reduce(red[:n])
-            buf[:] = red[:n].cpu().numpy()
-        mci.setAllreduce(allreduce)
 
     def barrier():
         if dist is not None:
@@ -235,7 +542,7 @@ def main():
     x0 = np.zeros((WALKERS_PER_GPU, 3))
     h2d = x0.nbytes
     nod = mci.getNObsDim()
-    d2h = 8*(3*nod) + 8 + 8*2*nod
+    d2h = 8*((5 if world > 1 else 3)*nod) + 8
     for _ in range(2):
         mci.setXWalkers(x0)
         mci.integrate(NMC, False, False)
@@ -248,6 +555,7 @@ def main():
     barrier()
     e2e_ms = maxreduce(1e3*(time.perf_counter() - t0))
     e2e_value = samples/(e2e_ms*1e-3)
+    cw_local = float(mci.crossWalkerError()[0])
 
     # ---- context for the roofline fraction (N = 1 only, outside every timed region): the named workload's 65536 walkers are 3.46 warps
     # per scheduler on 148 SMs; the same kernel with every scheduler holding 8 warps shows what the instruction stream itself allows
@@ -267,25 +575,43 @@ def main():
         full = (wfull, float(wfull)*NMC/(mf.timings()["walk_ms"]*1e-3))
         del mf
 
+    # ---- secondary workloads (outside the timed headline region)
+    secondary = None
+    pool = None
+    if not args.no_secondary:
+        if rank == 0 and not args.no_cpu_baseline:
+            pool = CpuPool()
+        secondary = {}
+        secondary["C5"] = secondary_c5(m, local, rank, world, peaks, pool, barrier, maxreduce)
+        secondary["strong_scaling"] = secondary_strong(m, local, rank, world, barrier, maxreduce)
+        if world == 1:
+            secondary["C3"] = secondary_c3(m, local, peaks, philox_peak, pool)
+            secondary["C4"] = secondary_c4(m, local, pool)
+
     if rank == 0:
         steps_per_s_kernel = float(WALKERS_PER_GPU)*NMC*args.steps/(walk_ms_max*1e-3)  # per GPU
         achieved = FP64_INSTR_PER_STEP*steps_per_s_kernel
+        sm_max_mhz = clocks.get("sm_max_mhz") or 1965.0
+        nominal = FP64_LANES_PER_SM*N_SM*sm_max_mhz*1e6
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": dev_ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rng": "Philox4x32-10, 32-bit uniforms", "walkers_per_gpu": WALKERS_PER_GPU, "nmc": NMC,
-                       "l2": "no HBM inputs to cache: walker state lives in registers; 1.5 MB of positions read once per step",
-                       "parallelism": "walkers sharded over %d GPU(s), 1 all-reduce of 2 doubles per integrate" % world},
+            "config": bench_config(world),
             "wall_ms_per_step": wall_ms/args.steps,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms/args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64_issue", "achieved": achieved/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s", "frac": achieved/peaks[0],
+                         "peak_nominal": nominal/1e9, "frac_nominal": achieved/nominal,
+                         "peak_nominal_source": "64 FP64 lanes/SM/clk x 148 SMs x %.0f MHz (clocks.max.sm); the measured DFMA microbenchmark reaches %.2f of it" % (sm_max_mhz, peaks[0]/nominal),
                          "traffic": WALK_DRAM_BYTES_PER_LAUNCH, "traffic_note": "dram__bytes_read + dram__bytes_write of one walk launch (ncu --set full, profiles/r01_walk_r1f_dyn_ncu_raw.csv): the 1.5 MB of start positions, nothing written; the bound is FP64/ALU issue, not HBM",
                          "kernel": "mcig_walk (JIT-specialised Metropolis walk)", "kernel_ms_per_step": walk_ms_max/args.steps,
                          "fp64_instr_per_metropolis_step": FP64_INSTR_PER_STEP, "flop_per_metropolis_step": FLOP_PER_STEP,
                          "achieved_tflops": FLOP_PER_STEP*steps_per_s_kernel/1e12, "peak_tflops": 2*peaks[0]/1e12,
                          "peak_source": "DFMA/s measured live by mcig_measure_peaks on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                          "imad_peak_ginst": peaks[1]/1e9,
+                         "ncu_pipes": {"source": "profiles/r01_walk_r1h_dyn_ncu_raw.csv (ncu --set full of this kernel; not re-measured inside bench.py)",
+                                       "fp64_pipe_active_pct": 16.7, "fma_heavy_pipe_active_pct": 62.1, "alu_pipe_active_pct": 54.2, "issue_slots_busy_pct": 61.3,
+                                       "note": "the kernel EXECUTES ~12 FP64 instructions per step (FP32 pre-filter of the accept test, cached observable); the 34 above are the algorithmic count the fraction is quoted on"},
                          "rng_bound": {"philox4x32_10_blocks_per_s": philox_peak, "blocks_per_step": 1, "frac": steps_per_s_kernel/philox_peak,
                                        "note": "issue-rate bound of the counter RNG alone (20 IMAD.WIDE.U32 at a quarter of the FP32 rate per block), measured live; "
                                                "the walk loop cannot exceed it whatever its FP64 content: context for the FP64 fraction above"},
@@ -293,16 +619,20 @@ def main():
                              "walkers": full[0], "steps_per_s": full[1], "frac": FP64_INSTR_PER_STEP*full[1]/peaks[0],
                              "note": "same kernel, 8 warps per scheduler instead of the workload's 3.46; context only, not the bench value"}},
             "clocks": clocks,
-            "result": {"avg": float(avg[0]), "err": float(err[0]), "acceptance": float(rate), "cross_walker_err_local": float(mci.crossWalkerError()[0])},
+            "result": {"avg": float(avg[0]), "err": float(err[0]), "acceptance": float(rate), "cross_walker_err_local": cw_local},
         }
-        if not args.no_cpu_baseline and world == 1:
-            nproc = os.cpu_count() or 1
-            v, kind, wall = cpu_reference_run(15000000, nproc)
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": nproc, "kind": kind,
-                                    "sample": "%d independent chains (one per host core) x 1.5e7 Metropolis steps of the same integrand, %.1f s wall" % (nproc, wall)}
+        if pool is not None and world == 1:
+            v, wall, outs = pool.run(c2_kw(), REF_NMC)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": pool.nproc, "kind": pool.kind,
+                                    "sample": "%d independent chains (one per host core) x %.1e Metropolis steps of the same integrand, %.1f s wall; %s" % (pool.nproc, REF_NMC, wall, pool.flags)}
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line))
+    if pool is not None:
+        pool.close()
     if dist is not None:
         dist.barrier()
+        parallel.finalize_comm()
         dist.destroy_process_group()
 
 

@@ -374,7 +374,9 @@ public:
     void setDevice(int device) { detail::check(mcig_set_device(_ctx, device)); }
     void setPhiloxRounds(int rounds) { detail::check(mcig_set_philox_rounds(_ctx, rounds)); }
     void setAllreduce(mcig_allreduce_fn fn, void * user) { detail::check(mcig_set_allreduce(_ctx, fn, user)); }
-    void getCrossWalkerError(double err[]) const { detail::check(mcig_get_cross_walker_error(_ctx, err)); }
+    void getCrossWalkerError(double err[]) const { detail::check(mcig_get_cross_walker_error(_ctx, err, mcig_get_result_nobsdim(_ctx))); }
+    void setKeepSamples(bool on) { detail::check(mcig_set_keep_samples(_ctx, on ? 1 : 0)); }
+    void attachComm(bool on = true) { detail::check(mcig_attach_comm(_ctx, on ? 1 : 0)); }
     void getWalkerResults(double avg[], double err[]) const { detail::check(mcig_get_walker_results(_ctx, avg, err)); }
     mcig_ctx * handle() const { return _ctx; }
 

@@ -149,6 +149,25 @@ int mcig_set_autotune(mcig_ctx * ctx, int nfind_iterations, int64_t ndecorrelati
 typedef void (*mcig_allreduce_fn)(double * buf, int n, void * user);
 int mcig_set_allreduce(mcig_ctx * ctx, mcig_allreduce_fn fn, void * user);
 
+/* ---- the collective inside the library: MPIMCI::init / myrank / size / finalize (src/MPIMCI.cpp:27-35, 95-104) for one process per GPU.
+ *      The communicator is process-global like MPI_COMM_WORLD (NCCL over NVLink / NVSwitch, libnccl.so.2 loaded on first use). Contexts that
+ *      are attached to it (mcig_attach_comm) run every MPI_Allreduce of the reference path — the rank-averaged acceptance rate of findMRT2Step
+ *      (src/MCIntegrator.cpp:131-138), the equilibration estimates (:21-34) and the final [sum avg | sum err^2] (src/MPIMCI.cpp:85-87) — as
+ *      ncclAllReduce on the engine's own stream over device memory, inside the device-resident control loops: no host hop per iteration.
+ *      mcig_comm_init_env: rank / size / device from RANK, WORLD_SIZE, LOCAL_RANK (or OMPI_COMM_WORLD_*), the ncclUniqueId travels over TCP
+ *      (MASTER_ADDR, MASTER_PORT + 17 or MCIG_COMM_PORT); a process started without WORLD_SIZE is a world of one and never loads NCCL.
+ *      mcig_comm_get_unique_id + mcig_comm_init_rank: the caller transports the 128-byte id itself (bench.py: torch.distributed broadcast).
+ *      Returns: init_env the rank (>= 0) or -(error code); the others 0 or an error code. */
+int mcig_comm_init_env(void);
+int mcig_comm_get_unique_id(void * id128);
+int mcig_comm_init_rank(const void * id128, int rank, int nranks, int device);
+int mcig_comm_rank(void);
+int mcig_comm_size(void);
+int mcig_comm_finalize(void);
+/* on = 1: this context is one rank's shard of a job over mcig_comm_size() processes; its device follows the communicator's. The walker
+ * shard itself is set with mcig_set_walkers(ctx, n_local, global_offset, total). */
+int mcig_attach_comm(mcig_ctx * ctx, int on);
+
 /* ---- MCI::integrate(Nmc, average, error, doFindMRT2step, doDecorrelation)  src/MCIntegrator.cpp:43-82, combined over
  *      walkers as MPIMCI::integrate does over ranks (src/MPIMCI.cpp:85-92): avg = sum_w avg_w / W, err = sqrt(sum_w err_w^2) / W */
 int mcig_integrate(mcig_ctx * ctx, int64_t nmc, double * average, double * error, int do_find_mrt2_step, int do_decorrelation);
@@ -158,12 +177,19 @@ double mcig_get_acceptance_rate(mcig_ctx * ctx);
 /* ---- results of the last integrate beyond the reference's API */
 int mcig_get_walker_results(mcig_ctx * ctx, double * avg /*[nobsdim][nwalkers]*/, double * err /*same*/);
 /* local sums [sum_w avg_w | sum_w err_w^2 | sum_w avg_w^2], 3*nobsdim doubles: the all-reduce payload of a sharded job */
-int mcig_get_sums(mcig_ctx * ctx, double * sums);
+int mcig_get_sums(mcig_ctx * ctx, double * sums, int capacity /* doubles the buffer holds: >= 3 * mcig_get_result_nobsdim */);
+/* number of observable components of the LAST integrate (the current configuration may have changed since: popObservable) */
+int mcig_get_result_nobsdim(mcig_ctx * ctx);
 /* standard error of the mean over walkers, sqrt((<a^2>-<a>^2)/(W-1)) (local walkers) */
-int mcig_get_cross_walker_error(mcig_ctx * ctx, double * err);
+int mcig_get_cross_walker_error(mcig_ctx * ctx, double * err, int capacity /* >= mcig_get_result_nobsdim */);
 /* stored samples of observable iobs of the last integrate (Block/Full accumulators), host order [nstore][nobs] of one walker */
 int64_t mcig_get_nstore(mcig_ctx * ctx, int iobs);
 int mcig_get_obs_data(mcig_ctx * ctx, int iobs, int64_t walker, double * data);
+/* The reference frees every accumulator at the end of integrate (src/MCIntegrator.cpp:79); this engine keeps what it stored until the next
+ * call, but a Block / Full accumulator whose estimator is the one-pass uncorrelated one (sum x, sum x^2: src/Estimators.cpp:36-56, 125-155)
+ * with at most 8 components does not store at all by default: the walker keeps both sums in registers, nothing is written to or re-read
+ * from HBM, and the results have the reference's summation order bit for bit. on = 1 keeps the series as well (for mcig_get_obs_data). */
+int mcig_set_keep_samples(mcig_ctx * ctx, int on);
 /* device times of the last integrate in ms (CUDA events on the engine's stream): the walk kernel of the main sampling run,
  * the estimation stage, the whole call (calibration + decorrelation + sampling + estimation); and the kernels it launched */
 int mcig_get_timings(mcig_ctx * ctx, double * walk_ms, double * estim_ms, double * total_ms, int64_t * kernel_launches);
@@ -184,11 +210,13 @@ int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 re
  * moves: add value x dwell time when a coordinate changes instead of every component at every step. 1 (default): in the Philox
  * modes, replay mode keeps the reference's summation order; 2: in every mode; 0: never. Sums differ by rounding only. */
 int mcig_set_lazy_accumulation(mcig_ctx * ctx, int on);
-/* findMRT2Step feedback loop on the device (default 1: sampling launch -> acceptance reduction -> controller kernel, no host
- * synchronisation per iteration; used in the Philox modes of a single-process job) or on the host (0: one 8-byte readback per
- * iteration; always used in replay mode and when a cross-process sum is installed). Same arithmetic, same results. */
+/* findMRT2Step and initialDecorrelation feedback loops on the device (default 1: sampling launch -> reduction / estimators -> [ncclAllReduce
+ * when attached to the communicator] -> controller kernel, enqueued in batches without a host synchronisation per iteration; Philox modes)
+ * or on the host (0: one readback per iteration; always used in replay mode and with a host mcig_set_allreduce callback).
+ * Same arithmetic, same results. */
 int mcig_set_device_calibration(mcig_ctx * ctx, int on);
 int mcig_get_calibration_iterations(mcig_ctx * ctx); /* iterations the last findMRT2Step executed */
+int mcig_get_decorrelation_chunks(mcig_ctx * ctx);   /* MIN_NMC-step chunks the last automatic initialDecorrelation sampled (src/MCIntegrator.cpp:193-241) */
 /* MCI::storeObservablesOnFile (what = 0) / storeWalkerPositionsOnFile (what = 1), src/MCIntegrator.cpp:495-542: text dump of
  * walker 0 every freq-th step of the main sampling run ("ridx v0 v1 ..."), written after the run from device-side shadow
  * accumulators. path NULL or "" switches the dump off (clearObservableFile / clearWalkerFile). */

@@ -58,8 +58,17 @@ SIGNATURES = {
     "mcig_integrate": (C.c_int, [_ctx, C.c_int64, _dp, _dp, C.c_int, C.c_int]),
     "mcig_get_acceptance_rate": (C.c_double, [_ctx]),
     "mcig_get_walker_results": (C.c_int, [_ctx, _dp, _dp]),
-    "mcig_get_sums": (C.c_int, [_ctx, _dp]),
-    "mcig_get_cross_walker_error": (C.c_int, [_ctx, _dp]),
+    "mcig_get_sums": (C.c_int, [_ctx, _dp, C.c_int]),
+    "mcig_get_result_nobsdim": (C.c_int, [_ctx]),
+    "mcig_get_cross_walker_error": (C.c_int, [_ctx, _dp, C.c_int]),
+    "mcig_set_keep_samples": (C.c_int, [_ctx, C.c_int]),
+    "mcig_comm_init_env": (C.c_int, []),
+    "mcig_comm_get_unique_id": (C.c_int, [C.c_void_p]),
+    "mcig_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mcig_comm_rank": (C.c_int, []),
+    "mcig_comm_size": (C.c_int, []),
+    "mcig_comm_finalize": (C.c_int, []),
+    "mcig_attach_comm": (C.c_int, [_ctx, C.c_int]),
     "mcig_get_nstore": (C.c_int64, [_ctx, C.c_int]),
     "mcig_get_obs_data": (C.c_int, [_ctx, C.c_int, C.c_int64, _dp]),
     "mcig_get_timings": (C.c_int, [_ctx, _dp, _dp, _dp, _i64p]),
@@ -73,6 +82,7 @@ SIGNATURES = {
     "mcig_set_lazy_accumulation": (C.c_int, [_ctx, C.c_int]),
     "mcig_set_device_calibration": (C.c_int, [_ctx, C.c_int]),
     "mcig_get_calibration_iterations": (C.c_int, [_ctx]),
+    "mcig_get_decorrelation_chunks": (C.c_int, [_ctx]),
     "mcig_store_on_file": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int]),
     "mcig_prebuild": (C.c_int, [_ctx]),
     "mcig_get_kernel_source": (C.c_int64, [_ctx, C.c_char_p, C.c_int64]),

@@ -183,6 +183,22 @@ __global__ void uncorr_finish_kernel(const double * __restrict__ part, i64 n, i6
     werr[col] = er;
 }
 
+// The same estimator when the walk kernel already accumulated sum x and sum x^2 of the stored values in its registers (FUSE in
+// device/mcig_device.cuh): one segment, the reference's left-to-right order, nothing read from the series.
+__global__ void uncorr_from_sums_kernel(const double * __restrict__ sums, const double * __restrict__ sqs, i64 n, i64 ncol, int nobs_is_one,
+                                        double * __restrict__ wavg, double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    const double norm = 1./(double)n;
+    const double avg = __dmul_rn(sums[col], norm);
+    double er = __dadd_rn(__dmul_rn(sqs[col], norm), -__dmul_rn(avg, avg));
+    if (er > 1.e-300) { er = nobs_is_one ? sqrt(er/((double)n - 1.)) : sqrt(__dmul_rn(er, 1./((double)n - 1.))); }
+    else { er = 0.; }
+    wavg[col] = avg;
+    werr[col] = er;
+}
+
 // ---------------------------------------------------------------------------------------------- K3 MJBlocker
 // Streaming blocking pyramid over one aligned segment of L = 2^m samples of one chain (thread = (segment, column)).
 // For every level k < m it accumulates sum X^2 and sum X_i X_{i+1} inside the segment and remembers the first and
@@ -851,6 +867,47 @@ __global__ void calib_controller_kernel(CalibCtl * __restrict__ ctl, const Calib
     ctl->group += (u64)a.steps_per_iter*(u64)a.groups_per_step;
     const bool again = ((a.N < 0 && cons < 5) || counter < a.N) && !(a.N < 0 && counter >= -a.N);
     ctl->done = again ? 0 : 1;
+}
+
+// The stopping rule of MCI::initialDecorrelation (src/MCIntegrator.cpp:193-241), one iteration, one block. comb = the combined estimates of the
+// chunk just sampled ([sum_w avg | sum_w err^2], already summed over the ranks of a sharded job), R = total number of walkers ("ranks").
+// st = [oldestimate[nod] | olderr[nod] | steps counted so far | warning flag]. Iteration 0 only records the first estimate (:199-202); iteration
+// it >= 1 adds MIN_NMC to the step count, stops with the warning when the maximum is reached (before estimating, as the reference does), else
+// compares with the previous chunk on 2 sigma and stops when every component agrees.
+struct DecorrArgs {
+    double R;
+    i64 min_nmc, max_steps;
+    int nod, groups_per_step;
+};
+__global__ void decorr_controller_kernel(CalibCtl * __restrict__ ctl, const double * __restrict__ comb, double * __restrict__ st, const DecorrArgs a)
+{
+    if (ctl->done != 0) { return; }
+    const int it = ctl->counter;
+    double * old = st, * olderr = st + a.nod;
+    const bool at_max = (it > 0) && ((i64)st[2*a.nod] + a.min_nmc >= a.max_steps);
+    int differs = 0;
+    if (!at_max) {
+        for (int i = threadIdx.x; i < a.nod; i += blockDim.x) {
+            const double nw = comb[i]/a.R, ne = sqrt(comb[a.nod + i])/a.R; // MPIMCI combination: src/MPIMCI.cpp:89-92
+            if (it > 0 && fabs(old[i] - nw) > 2*sqrt(__dadd_rn(__dmul_rn(olderr[i], olderr[i]), __dmul_rn(ne, ne)))) { differs = 1; }
+            old[i] = nw;
+            olderr[i] = ne;
+        }
+    }
+    const int any = __syncthreads_or(differs);
+    if (threadIdx.x == 0) {
+        ctl->group += (u64)a.min_nmc*(u64)a.groups_per_step;
+        ctl->executed += 1;
+        ctl->counter = it + 1;
+        if (it > 0) {
+            st[2*a.nod] += (double)a.min_nmc;
+            if (at_max) {
+                st[2*a.nod + 1] = 1.;
+                ctl->done = 1;
+            }
+            else if (!any) { ctl->done = 1; }
+        }
+    }
 }
 
 // ready-queue of the dynamically scheduled walk kernel: chunk 0 of every walker block is ready, the rest is produced at run time

@@ -309,21 +309,32 @@ class MCI:
         _capi.check(self._lib.mcig_set_allreduce(self._ctx, self._cb, None))
 
     def walkerResults(self):
-        nod, W = self.getNObsDim(), self.getNWalkers()
+        nod, W = self._lib.mcig_get_result_nobsdim(self._ctx), self.getNWalkers()
         avg = np.zeros((nod, W))
         err = np.zeros((nod, W))
         _capi.check(self._lib.mcig_get_walker_results(self._ctx, avg.ctypes.data_as(_dp), err.ctypes.data_as(_dp)))
         return avg, err
 
     def sums(self):
-        s = np.zeros(3*max(1, self.getNObsDim()))
-        _capi.check(self._lib.mcig_get_sums(self._ctx, s.ctypes.data_as(_dp)))
-        return s[:3*self.getNObsDim()]
+        nod = self._lib.mcig_get_result_nobsdim(self._ctx)  # of the last integrate: the observable list may have changed since
+        s = np.zeros(3*max(1, nod))
+        _capi.check(self._lib.mcig_get_sums(self._ctx, s.ctypes.data_as(_dp), len(s)))
+        return s[:3*nod]
 
     def crossWalkerError(self):
-        e = np.zeros(max(1, self.getNObsDim()))
-        _capi.check(self._lib.mcig_get_cross_walker_error(self._ctx, e.ctypes.data_as(_dp)))
-        return e[:self.getNObsDim()]
+        nod = self._lib.mcig_get_result_nobsdim(self._ctx)
+        e = np.zeros(max(1, nod))
+        _capi.check(self._lib.mcig_get_cross_walker_error(self._ctx, e.ctypes.data_as(_dp), len(e)))
+        return e[:nod]
+
+    def setKeepSamples(self, on=True):
+        """Keep the stored series of Block / Full accumulators whose one-pass estimator runs inside the walk kernel (for obsData)."""
+        _capi.check(self._lib.mcig_set_keep_samples(self._ctx, int(bool(on))))
+
+    def attachComm(self, on=True):
+        """This MCI is one rank's shard of a job over comm_size() processes: every all-reduce of the path runs as ncclAllReduce on the
+        engine's stream (see parallel.init_comm)."""
+        _capi.check(self._lib.mcig_attach_comm(self._ctx, int(bool(on))))
 
     def obsData(self, iobs, walker=0, nobs=1):
         nstore = self._lib.mcig_get_nstore(self._ctx, int(iobs))
@@ -349,6 +360,7 @@ class MCI:
     def setLazyAccumulation(self, on): _capi.check(self._lib.mcig_set_lazy_accumulation(self._ctx, int(on)))
     def setDeviceCalibration(self, on): _capi.check(self._lib.mcig_set_device_calibration(self._ctx, int(on)))
     def getCalibrationIterations(self): return self._lib.mcig_get_calibration_iterations(self._ctx)
+    def getDecorrelationChunks(self): return self._lib.mcig_get_decorrelation_chunks(self._ctx)
     def setPhiloxRounds(self, rounds): _capi.check(self._lib.mcig_set_philox_rounds(self._ctx, int(rounds)))
     def setDynamicScheduling(self, mode): _capi.check(self._lib.mcig_set_dynamic_scheduling(self._ctx, int(mode)))
     def prebuild(self): _capi.check(self._lib.mcig_prebuild(self._ctx))

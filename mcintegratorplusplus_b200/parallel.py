@@ -57,15 +57,53 @@ def combine(sums, nobsdim, total_walkers):
     return avg, err
 
 
+def init_comm(device=None):
+    """Create the library's own NCCL communicator (include/mcig.h: mcig_comm_*) for the ranks of the initialised torch.distributed job:
+    rank 0 draws the ncclUniqueId, torch.distributed only transports its 128 bytes. Afterwards MCI.attachComm() makes every all-reduce of
+    the sampling path an ncclAllReduce on the engine's stream, inside the device-resident control loops. Returns (rank, world)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _capi
+    lib = _capi.lib()
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0, 1
+    if lib.mcig_comm_size() > 1:
+        return lib.mcig_comm_rank(), lib.mcig_comm_size()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = torch.cuda.current_device()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _capi.check(lib.mcig_comm_get_unique_id(buf))
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().numpy().tobytes())
+    _capi.check(lib.mcig_comm_init_rank(C.create_string_buffer(raw, 128), rank, world, int(device)))
+    return rank, world
+
+
+def finalize_comm():
+    from . import _capi
+    _capi.check(_capi.lib().mcig_comm_finalize())
+
+
 def install(mci, total_walkers, group=None):
-    """Give `mci` its shard of `total_walkers` and the cross-rank sum. Returns (n_local, offset)."""
+    """Give `mci` its shard of `total_walkers` and the cross-rank sum. Returns (n_local, offset). On GPUs (NCCL backend, default group)
+    the sum is the library's own ncclAllReduce (init_comm + attachComm); otherwise (gloo in the CPU tests, sub-groups) a host callback."""
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n, off = shard(total_walkers, rank, world)
     mci.setNWalkers(n, global_offset=off, total=total_walkers)
     if world > 1:
-        mci.setAllreduce(lambda buf: allreduce_sum(buf, group))
+        if group is None and dist.get_backend() == "nccl":
+            init_comm()
+            mci.attachComm()
+        else:
+            mci.setAllreduce(lambda buf: allreduce_sum(buf, group))
     return n, off
 
 

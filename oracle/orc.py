@@ -196,6 +196,26 @@ def have_ref():
     return os.path.exists(REF_PATH)
 
 
+def ref_timing_path():
+    """The timing build of the unmodified reference best matched to THIS host's CPU (oracle/Makefile: -O3 -march=x86-64-v4 / -v3 unity builds,
+    the portable spelling of the reference's own -march=native), falling back to the parity build. Returns (path, flags description)."""
+    flags = set()
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = set(line.split(":", 1)[1].split())
+                break
+    except OSError:
+        pass
+    v3 = {"avx2", "fma", "bmi2", "bmi1", "movbe", "f16c", "abm"} <= flags
+    v4 = v3 and {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
+    for ok, name, desc in ((v4, "libmci_ref_v4.so", "-O3 -march=x86-64-v4, all reference sources as one translation unit (whole-program, in place of -flto)"), (v3, "libmci_ref_v3.so", "-O3 -march=x86-64-v3, all reference sources as one translation unit (whole-program, in place of -flto)")):
+        path = os.path.join(HERE, "_ref", name)
+        if ok and os.path.exists(path):
+            return path, desc
+    return REF_PATH, "-O3 -ffp-contract=off (generic x86-64)"
+
+
 def ref():
     return Engine(REF_PATH, "mciref")
 

@@ -72,6 +72,7 @@ def test_full_accumulator_round_trip_at_scale(mcig):
     base = dict(ndim=3, seed=99, pdf_id=orc.PDF_GAUSS3D, nmc=1 << 14, steps=(1.0,))
     m1 = build_mci(mcig, dict(base, obs=[(orc.OBS_XSQUARED, 0, 1), (orc.OBS_XSQUARED, 1, 1, False, orc.EST_UNCORRELATED),
                                          (orc.OBS_XSQUARED, 16, 1, False, orc.EST_UNCORRELATED)]), nwalkers=8192, mode=0)
+    m1.setKeepSamples(True)
     avg, err = m1.integrate(1 << 14, False, False)
     wavg, _ = m1.walkerResults()
     assert np.allclose(wavg[0], wavg[1], rtol=1e-13, atol=0) and np.allclose(wavg[0], wavg[2], rtol=1e-13, atol=0)

@@ -118,6 +118,7 @@ def test_accept_sequence_and_trajectory_bit_exact(mcig, oracle):
             x = x + 1.0*draws[t, :3]
         traj[t] = x
     mci = build_mci(mcig, spec)
+    mci.setKeepSamples(True)  # the uncorrelated estimator of a small observable runs inside the walk; keep the series for this check
     mci.integrate(nmc, False, False)
     data = mci.obsData(0, walker=0, nobs=3)
     assert data.shape == (nmc, 3)
@@ -135,6 +136,7 @@ def test_vec_move_accept_sequence(mcig, oracle):
     tr = oracle.run(cfg, trace=True)
     for placement in (0, 1):
         mci = build_mci(mcig, spec, placement=placement)
+        mci.setKeepSamples(True)
         mci.integrate(nmc, False, False)
         data = mci.obsData(0, walker=0, nobs=4)
         prev = np.vstack([np.array(spec["x0"])[None, :], data[:-1]])
@@ -372,3 +374,35 @@ def test_lazy_accumulation_against_the_reference(name, mcig, golden_runs):
     scale = max(1.0, float(np.max(np.abs(ref))))
     assert np.max(np.abs(avg - ref)) <= 1e-12*scale, np.max(np.abs(avg - ref))
     assert _close(err, fromhex(g["err"]), 1e-9, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["block16", "full_uncorr", "mixed", "block_skip_big", "tp3g_small", "gauss_all", "srrd_gamma_vec", "full_two_samples"])
+@pytest.mark.parametrize("dyn", [0, 1])
+def test_fused_one_pass_estimator_is_the_reference_bit_for_bit(name, dyn, mcig, oracle, golden_runs):
+    """Block / Full accumulators with the uncorrelated estimator never touch HBM: the walker keeps sum x and sum x^2 of what it would have
+    stored (src/Estimators.cpp:36-56, 125-155: one pass, left to right) in registers. In replay mode averages AND errors are then the
+    reference's to the last bit where the estimator is the 1-D one (std::accumulate / inner_product order), and within the usual
+    tolerances otherwise; keeping the series as well (setKeepSamples) must not change a bit, nor may the chunked (dynamic) schedule."""
+    spec = configs.RUNS[name]
+    g = golden_runs[name]
+    if name in ("srrd_gamma_vec",) and dyn:
+        pytest.skip("state-memory walkers have no dynamically scheduled kernel")
+    res = []
+    for keep in (False, True):
+        mci = build_mci(mcig, spec)
+        mci.setKeepSamples(keep)
+        if dyn:
+            mci.setStatePlacement(0)
+            mci.setDynamicScheduling(1)
+        avg, err = mci.integrate(spec["nmc"], False, False)
+        src = mci.kernelSource()
+        assert ("Accu<" in src) and ((",2> a" in src or ",2,false> a" in src) != keep)
+        res.append((avg.copy(), err.copy()))
+        if not keep:
+            from mcintegratorplusplus_b200._capi import McigError
+            fused = [i for i, o in enumerate(spec["obs"]) if tuple(o)[1] >= 1 and (tuple(o)[4] if len(tuple(o)) > 4 else orc.default_estim(tuple(o)[1])) == orc.EST_UNCORRELATED]
+            assert fused
+            with pytest.raises(McigError, match="were not stored"):
+                mci.obsData(fused[0], walker=0, nobs=1)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert _close(res[0][0], fromhex(g["avg"]), AVG_RTOL) and _close(res[0][1], fromhex(g["err"]), ERR_RTOL, atol=1e-18)
