@@ -317,7 +317,7 @@ def secondary_c3(m, local, peaks, philox_peak, pool):
                    "roofline": {"bound": "fp64_issue", "fp64_instr_per_step": instr, "achieved": instr*sps/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s",
                                 "frac": instr*sps/peaks[0], "philox_blocks_per_step": blocks, "rng_frac": blocks*sps/philox_peak}}
             if pool is not None:
-                nmc_cpu = max(2000, int({"vec": 3e6/(1 + nd/6.0), "all": 3e6/(1 + nd/1.5)}.get(move, 3e6/(1 + 6.0*nd)))//20*20)
+                nmc_cpu = max(2000, int({"vec": 2.4e7/(1 + nd/6.0), "all": 2.4e7/(1 + nd/1.5)}.get(move, 2.4e7/(1 + 6.0*nd)))//20*20)  # ~0.2-1 s per chain
                 v, wall, _ = pool.run(c3_kw(move, nd), nmc_cpu)
                 row["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": pool.nproc, "kind": pool.kind,
                                        "sample": "%d chains x %d steps, %.2f s" % (pool.nproc, nmc_cpu, wall)}
@@ -441,9 +441,9 @@ def secondary_c5(m, local, rank, world, peaks, pool, barrier, maxreduce):
         orc = _orc_ids()
         kw = dict(ndim=3, seed=5649871, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_XSQUARED, 1, 5), (orc.OBS_XYZSQUARED, 5, 2)], steps=(1.0,),
                   do_find=True, do_decorr=True)
-        v, wall, _ = pool.run(kw, 2000000)
+        v, wall, _ = pool.run(kw, 10000000)
         out["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": pool.nproc, "kind": pool.kind,
-                               "sample": "%d chains x 2e6 steps incl. calibration + decorrelation, %.2f s" % (pool.nproc, wall)}
+                               "sample": "%d chains x 1e7 steps incl. calibration + decorrelation, %.2f s" % (pool.nproc, wall)}
     del mci
     return out
 
@@ -492,8 +492,14 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        parallel.init_comm(local)  # the library's own NCCL communicator (id broadcast through torch.distributed)
+        saved = os.dup(1)  # NCCL announces its version on stdout at the first communicator: keep stdout for the one JSON line
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            parallel.init_comm(local)  # the library's own NCCL communicator (id broadcast through torch.distributed)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     mci = make_mci(m, rank, world)
 

@@ -216,6 +216,10 @@ int mcig_set_lazy_accumulation(mcig_ctx * ctx, int on);
  * Same arithmetic, same results. */
 int mcig_set_device_calibration(mcig_ctx * ctx, int on);
 int mcig_get_calibration_iterations(mcig_ctx * ctx); /* iterations the last findMRT2Step executed */
+/* Launches the last main sampling run was split into: 0 = one launch with every stored series resident in HBM; n > 0 = the series did not fit
+ * (include/mci/FullAccumulator.hpp:11-13) and was sampled, staged in a double buffer and folded into the estimators' state chunk by chunk
+ * (MJBlocker, uncorrelated and Noop estimators; Philox modes, register-resident walkers; anything else fails loudly with the size). */
+int64_t mcig_get_staging_chunks(mcig_ctx * ctx);
 int mcig_get_decorrelation_chunks(mcig_ctx * ctx);   /* MIN_NMC-step chunks the last automatic initialDecorrelation sampled (src/MCIntegrator.cpp:193-241) */
 /* MCI::storeObservablesOnFile (what = 0) / storeWalkerPositionsOnFile (what = 1), src/MCIntegrator.cpp:495-542: text dump of
  * walker 0 every freq-th step of the main sampling run ("ridx v0 v1 ..."), written after the run from device-side shadow

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mcig_set_device_calibration": (C.c_int, [_ctx, C.c_int]),
     "mcig_get_calibration_iterations": (C.c_int, [_ctx]),
     "mcig_get_decorrelation_chunks": (C.c_int, [_ctx]),
+    "mcig_get_staging_chunks": (C.c_int64, [_ctx]),
     "mcig_store_on_file": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int]),
     "mcig_prebuild": (C.c_int, [_ctx]),
     "mcig_get_kernel_source": (C.c_int64, [_ctx, C.c_char_p, C.c_int64]),

@@ -453,6 +453,110 @@ __global__ void mj_finish_kernel(const double * __restrict__ lvl, const double *
     werr[col] = (k >= npow) ? 0. : sqrt(var[k]/exp2((double)(npow - k)));
 }
 
+// ---- chunked staging (a series longer than HBM is sampled, staged and folded chunk by chunk; include/mci/FullAccumulator.hpp:11-13 warns
+// about exactly this memory need). The blocker centres every level on the GLOBAL mean (src/MJBlocker.cpp:70-103), which is only known after the
+// last chunk; the chunks are therefore centred on a provisional mean mu0 (the mean of the first chunk) and the level statistics corrected
+// exactly at the end: with X = x - mu0, Y = x - mu = X - d (d = mu - mu0) and sum_i X_i = n_k d on every level,
+//     sum Y_i^2       = sum X_i^2 - n_k d^2
+//     sum Y_i Y_{i+1} = sum X_i X_{i+1} - (n_k + 1) d^2 + d (X_first + X_last).
+// d is of the order sigma/sqrt(chunk length): the correction terms are far below the rounding of the sums (errors stay inside 1e-9).
+
+// One thread per (chain, level < m): folds the segments of ONE chunk into the running statistics of that level, in time order.
+// acc[(k*4 + {sq, cr, firstX (of the whole series), lastX})*ncol + col]
+__global__ void mj_merge_accum_kernel(const double * __restrict__ seg_out, i64 ncol, i64 nseg, int m, int first_chunk, double * __restrict__ acc)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    const int k = (int)blockIdx.y;
+    double * a = acc + (i64)(k*4)*ncol + col;
+    double sq = 0., cr = 0., firstX = 0., lastX = 0.;
+    if (!first_chunk) {
+        sq = a[0];
+        cr = a[ncol];
+        firstX = a[2*ncol];
+        lastX = a[3*ncol];
+    }
+    for (i64 s = 0; s < nseg; ++s) {
+        const double * o = seg_out + ((s*m + k)*4)*ncol + col;
+        const double o0 = __ldcs(o), o1 = __ldcs(o + ncol), o2 = __ldcs(o + 2*ncol), o3 = __ldcs(o + 3*ncol);
+        if (first_chunk && s == 0) { firstX = o2; }
+        else { cr = __dadd_rn(cr, __dmul_rn(lastX, o2)); } // product across the segment / chunk border
+        sq = __dadd_rn(sq, o0);
+        cr = __dadd_rn(cr, o1);
+        lastX = o3;
+    }
+    a[0] = sq;
+    a[ncol] = cr;
+    a[2*ncol] = firstX;
+    a[3*ncol] = lastX;
+}
+
+// One thread per chain: levels < m from the folded statistics (with the mean correction above), levels >= m from the pyramid over all
+// segment tops of all chunks (uncentred segment means: centred on the true mean here), then the level choice of src/MJBlocker.cpp:106-152.
+__global__ void mj_finish_shifted_kernel(const double * __restrict__ acc, const double * __restrict__ top, i64 ncol, i64 n, i64 nseg, int m, int npow,
+                                         const double * __restrict__ mu0, const double * __restrict__ sums, double * __restrict__ wavg, double * __restrict__ werr)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    double var[MCIG_MJ_MAXLEV], gam[MCIG_MJ_MAXLEV];
+    const double mu = sums[col]/(double)n; // src/MJBlocker.cpp:46-55: input-order sum, then one division
+    const double d = __dadd_rn(mu, -mu0[col]);
+    const double d2 = __dmul_rn(d, d);
+    for (int k = 0; k < m; ++k) {
+        const double * a = acc + (i64)(k*4)*ncol + col;
+        const double nred = (double)(n >> k);
+        var[k] = __dadd_rn(a[0], -__dmul_rn(nred, d2))/nred;
+        gam[k] = __dadd_rn(__dadd_rn(a[ncol], -__dmul_rn(nred + 1., d2)), __dmul_rn(d, __dadd_rn(a[2*ncol], a[3*ncol])))/nred;
+    }
+    {
+        MJLevel lv[MCIG_MJ_MAXLEV];
+        const int mt = npow - m;
+        for (int k = 0; k < mt; ++k) { lv[k].sq = 0.; lv[k].cr = 0.; lv[k].firstX = 0.; lv[k].prevX = 0.; lv[k].pend = 0.; }
+        unsigned long long have = 0, cnt = 0;
+        double t = 0.;
+        for (i64 s = 0; s < nseg; ++s) { mj_push(lv, have, cnt, mt, __ldcs(top + s*ncol + col), mu, t); }
+        for (int k = 0; k < mt; ++k) {
+            const double nred = (double)(n >> (m + k));
+            var[m + k] = lv[k].sq/nred;
+            gam[m + k] = lv[k].cr/nred;
+        }
+    }
+    double M[MCIG_MJ_MAXLEV];
+    for (int i = 0; i < npow; ++i) {
+        const double q = gam[i]/var[i];
+        M[npow - i - 1] = __dmul_rn(__dmul_rn(q, q), exp2((double)(npow - i)));
+    }
+    int kk = -1;
+    {
+        double Msum[MCIG_MJ_MAXLEV];
+        double run = 0.;
+        for (int i = 0; i < npow; ++i) {
+            run = __dadd_rn(run, M[i]);
+            Msum[i] = run;
+        }
+        for (kk = npow - 1; kk >= 0; --kk) {
+            if (Msum[kk] < c_mj_quantile[kk]) { break; }
+        }
+    }
+    const int k = npow - (kk + 1);
+    wavg[col] = mu;
+    werr[col] = (k >= npow) ? 0. : sqrt(var[k]/exp2((double)(npow - k)));
+}
+
+// running [sum x | sum x^2] of a chain over the chunks, from one chunk's per-segment partials (uncorrelated estimator, many components)
+__global__ void uncorr_accum_kernel(const double * __restrict__ part, i64 ncol, int nseg, int first_chunk, double * __restrict__ acc /*[2][ncol]*/)
+{
+    const i64 col = (i64)blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= ncol) { return; }
+    double s = first_chunk ? 0. : acc[col], q = first_chunk ? 0. : acc[ncol + col];
+    for (int seg = 0; seg < nseg; ++seg) {
+        s = __dadd_rn(s, part[((i64)seg*2 + 0)*ncol + col]);
+        q = __dadd_rn(q, part[((i64)seg*2 + 1)*ncol + col]);
+    }
+    acc[col] = s;
+    acc[ncol + col] = q;
+}
+
 // mean of stored data per column from the in-kernel running sums: mean = sum / n  (src/MJBlocker.cpp:46-55 divides)
 __global__ void mean_from_sum_kernel(const double * __restrict__ sums, i64 ncol, double n, double * __restrict__ mean)
 {

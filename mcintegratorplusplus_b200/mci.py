@@ -361,6 +361,7 @@ class MCI:
     def setDeviceCalibration(self, on): _capi.check(self._lib.mcig_set_device_calibration(self._ctx, int(on)))
     def getCalibrationIterations(self): return self._lib.mcig_get_calibration_iterations(self._ctx)
     def getDecorrelationChunks(self): return self._lib.mcig_get_decorrelation_chunks(self._ctx)
+    def getStagingChunks(self): return self._lib.mcig_get_staging_chunks(self._ctx)
     def setPhiloxRounds(self, rounds): _capi.check(self._lib.mcig_set_philox_rounds(self._ctx, int(rounds)))
     def setDynamicScheduling(self, mode): _capi.check(self._lib.mcig_set_dynamic_scheduling(self._ctx, int(mode)))
     def prebuild(self): _capi.check(self._lib.mcig_prebuild(self._ctx))

@@ -140,3 +140,47 @@ def test_c4_full_accumulator_mjblocker_through_the_walk(mcig, oracle):
     assert avg[0] == pytest.approx(wavg[0].sum()/W, rel=1e-13)
     assert err[0] == pytest.approx(np.sqrt((werr[0]**2).sum())/W, rel=1e-12)
     assert abs(avg[0] - 0.5) < 4*err[0]
+
+
+def test_chunked_staging_equals_resident_series(mcig, oracle, monkeypatch):
+    """A stored series that does not fit HBM is sampled, staged and folded chunk by chunk (include/mci/FullAccumulator.hpp:11-13 warns about
+    the memory; src/MJBlocker.cpp:46-154 needs the global mean, which the chunks only know at the end). Forced here on a small run with
+    MCIG_CHUNK_BYTES: per-walker means must be the resident run's to rounding, MJBlocker errors to 1e-9 (the folded level sums are centred
+    on the first chunk's mean and corrected exactly), Noop / fused observables and the chain itself must not change at all; one chain is also
+    checked against the oracle's own MJBlocker."""
+    from prod import build_mci
+    W, k = 2048, 16
+    spec = dict(ndim=3, seed=77, pdf_id=orc.PDF_GAUSS3D, nmc=1 << k, steps=(1.0,),
+                obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_MJBLOCKER), (orc.OBS_XYZSQUARED, 4, 2, False, orc.EST_MJBLOCKER), (orc.OBS_XND, 0, 1),
+                     (orc.OBS_XYZSQUARED, 1, 4, False, orc.EST_UNCORRELATED), (orc.OBS_XSQUARED, 1, 8, False, orc.EST_NOOP)])
+    out = []
+    for budget in (None, 96 << 20):
+        if budget:
+            monkeypatch.setenv("MCIG_CHUNK_BYTES", str(budget))
+        else:
+            monkeypatch.delenv("MCIG_CHUNK_BYTES", raising=False)
+        mci = build_mci(mcig, spec, nwalkers=W, mode=0)
+        mci.setKeepSamples(not budget)
+        mci.integrate(1 << 12, False, False)   # chains continue from wherever the first call left them
+        avg, err = mci.integrate(1 << k, False, False)
+        wavg, werr = mci.walkerResults()
+        x = mci.obsData(0, walker=5, nobs=1)[:, 0] if not budget else None
+        out.append((avg.copy(), err.copy(), wavg.copy(), werr.copy(), mci.getAcceptanceRate(), [list(mci.getX(walker=w)) for w in (0, 999, W - 1)], mci.getStagingChunks(), x))
+        if budget:
+            from mcintegratorplusplus_b200._capi import McigError
+            with pytest.raises(McigError, match="were not stored"):
+                mci.obsData(0, walker=5, nobs=1)
+    a, b = out
+    assert a[6] == 0 and b[6] >= 4
+    assert a[4] == b[4] and a[5] == b[5]
+    assert np.allclose(a[2], b[2], rtol=1e-13, atol=1e-16)
+    assert np.allclose(a[3], b[3], rtol=1e-9, atol=1e-18)
+    assert np.array_equal(a[2][4:7], b[2][4:7]) and np.array_equal(a[2][10], b[2][10])  # Simple and Noop legs: bit-identical
+    assert np.allclose(a[0], b[0], rtol=1e-13, atol=1e-16) and np.allclose(a[1], b[1], rtol=1e-9, atol=1e-18)
+    av, er = oracle.estimate(orc.EST_MJBLOCKER, a[7])
+    assert b[2][0, 5] == pytest.approx(av[0], rel=1e-12) and b[3][0, 5] == pytest.approx(er[0], rel=1e-9)
+    monkeypatch.setenv("MCIG_CHUNK_BYTES", str(96 << 20))
+    mci = build_mci(mcig, dict(spec, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=60000*8), nwalkers=W, mode=0)  # Correlated on a non power of two: FCBlocker
+    from mcintegratorplusplus_b200._capi import McigError
+    with pytest.raises(McigError, match="chunked staging"):
+        mci.integrate(60000*8, False, False)

@@ -108,3 +108,28 @@ def test_c4_full_size_chain_blocks_through_the_walk(mcig, oracle):
     assert wavg[0, w] == pytest.approx(a[0], rel=1e-12) and werr[0, w] == pytest.approx(e[0], rel=1e-9)
     assert abs(avg[0] - 0.5) < 4*err[0] and err[0] < 2e-5*np.sqrt(128/W)
     del mci
+
+
+def test_c4_series_beyond_hbm_chunked_staging(mcig, oracle):
+    """65536 chains x 2^20 stored samples = 550 GB of series on a 180 GB device (BASELINE configs[3] with device-side HBM staging): sampled,
+    staged and folded chunk by chunk. One chain is re-run alone (Philox streams are keyed by the global walker id, so walker w of the big job
+    and a one-walker job at global offset w are the same chain), its resident series goes through the oracle's MJBlocker
+    (src/MJBlocker.cpp:127-154): mean 1e-12, error 1e-9."""
+    W, k, w = 65536, 20, 40961
+    spec = dict(ndim=3, seed=2029, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1, False, orc.EST_MJBLOCKER)], nmc=1 << k, steps=(1.0,))
+    mci = build_mci(mcig, spec, nwalkers=W, mode=0)
+    avg, err = mci.integrate(1 << k, False, False)
+    assert mci.getStagingChunks() >= 4
+    wavg, werr = mci.walkerResults()
+    t = mci.timings()
+    del mci
+    one = build_mci(mcig, spec, mode=0)
+    one.setNWalkers(1, global_offset=w, total=W)
+    one.setKeepSamples(True)
+    one.integrate(1 << k, False, False)
+    x = one.obsData(0, walker=0, nobs=1)[:, 0]
+    a, e = oracle.estimate(orc.EST_MJBLOCKER, x)
+    assert wavg[0, w] == pytest.approx(a[0], rel=1e-12) and werr[0, w] == pytest.approx(e[0], rel=1e-9)
+    assert abs(avg[0] - 0.5) < 4*err[0] and err[0] < 1e-5
+    assert avg[0] == pytest.approx(wavg[0].sum()/W, rel=1e-13)
+    assert t["total_ms"] < 5000
