@@ -55,6 +55,9 @@ enum {
                                      * reads (with HAS_UPDATE the new values of a selective update may live in registers, not in an array) */
     MCIG_PLUGIN_LOG_ACCEPTANCE = 4, /* functor provides logAcceptance(protoold, protonew) = log(acceptanceFunction) */
     MCIG_PLUGIN_PROTO_ELEMENT = 16, /* sampling function (with ELEMENTWISE | HAS_UPDATE) provides protoElement(x_k) = proto value k */
+    MCIG_PLUGIN_SUM_ACCEPTANCE = 32,/* sampling function (with PROTO_ELEMENT): acceptanceFunction(po, pn) = exp(sum_k po[k] - sum_k pn[k]), both sums in index
+                                     * order from 0 (Gauss, ExpNDPDF: test/common/TestMCIFunctions.hpp:173-177, 240-245). All-moves over >= 64 coordinates then
+                                     * spread one walker over several lanes of a warp, each summing its share (state placement 3) */
     MCIG_PLUGIN_DEPENDENT = 8       /* observable: observableFunction(x, out, dep) with dep.proto(i) / dep.obs(k, j) (DependentObservableInterface) */
 };
 
@@ -205,7 +208,9 @@ int mcig_estimate_blocks(int64_t n, int ndim, const double * x, int64_t nblocks,
 
 /* ---- engine knobs without reference analogue */
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
-int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory, 2 global memory (auto picks 2 when a warp of walkers exceeds 227 KiB) */
+int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory, 2 global memory (auto picks 2 when a warp of walkers exceeds 227 KiB),
+                                                                  * 3 registers of several lanes per walker (uniform all-moves with a SUM_ACCEPTANCE sampling function and
+                                                                  * element-wise observables; auto picks it from 64 coordinates on) */
 /* Element-wise observables (plugin flag MCIG_PLUGIN_ELEMENTWISE, e.g. XND, X2) in Simple / Block accumulators under single-vector
  * moves: add value x dwell time when a coordinate changes instead of every component at every step. 1 (default): in the Philox
  * modes, replay mode keeps the reference's summation order; 2: in every mode; 0: never. Sums differ by rounding only. */

@@ -88,10 +88,11 @@ class StepCallback(Plugin):
 
 
 def register_plugin(kind, name, type_expr, source, ndim=0, nvalues=0, npar=0, has_update=False, elementwise=False, log_acceptance=False,
-                    dependent=False):
+                    dependent=False, proto_element=False, sum_acceptance=False):
     """Register a user functor (CUDA C++ source, see csrc/device/mcig_functors.cuh for the contract).
     kind: 0 sampling function, 1 observable (dependent=True: DependentObservableInterface), 2 step callback."""
-    flags = (1 if has_update else 0) | (2 if elementwise else 0) | (4 if log_acceptance else 0) | (8 if dependent else 0)
+    flags = ((1 if has_update else 0) | (2 if elementwise else 0) | (4 if log_acceptance else 0) | (8 if dependent else 0) | (16 if proto_element else 0) |
+             (32 if sum_acceptance else 0))
     pid = _capi.lib().mcig_register_plugin(kind, name.encode(), type_expr.encode(), (source or "").encode(), ndim, nvalues, npar, flags)
     if pid < 0:
         raise _capi.McigError(-pid, _capi.lib().mcig_last_error().decode())

@@ -101,6 +101,11 @@ RUNS = {
                            x0=_alt(32)),
     "ndim_vec64_b20": dict(ndim=64, seed=6405, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 20, 1)], nmc=20000, move_type=orc.MOVE_VEC, veclen=1, steps=(3.0,),
                            x0=_alt(64)),
+    # --- lane-split walkers (state placement 3, automatic for eligible all-moves from ndim 64 on): typed steps, periodic domain, Simple / Full /
+    #     Block accumulators of element-wise observables, automatic calibration + decorrelation
+    "lanes_all128_auto": dict(ndim=128, seed=12801, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_X2, 1, 2), (orc.OBS_UPDXND, 8, 1)], nmc=4096,
+                              ntypes=2, type_ends=[64, 128], steps=(0.2, 0.1), lb=-3., ub=3., x0=_alt(128), nfind=-20, ndecorr=-2000, do_find=True, do_decorr=True),
+    "lanes_all192": dict(ndim=192, seed=19201, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_X2, 16, 1, True, orc.EST_CORRELATED)], nmc=2048, steps=(0.15,), x0=_alt(192)),
     # --- Gaussian proposals (SRRDType::Gaussian: std::normal_distribution, polar method with a cached value)
     "gauss_all": dict(ndim=3, seed=99, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 16, 1)], nmc=16384, srrd=orc.SRRD_GAUSSIAN, steps=(0.6,)),
     "gauss_all_auto": dict(ndim=3, seed=98, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=8192, srrd=orc.SRRD_GAUSSIAN, x0=(2., -2., 1.),
@@ -158,6 +163,9 @@ def in_oracle(name):
 # the C3 shapes whose kernels are footprint- / register-limited: replayed on every state placement (tests/test_walk_parity.py)
 C3_SHAPES = ["ms_sub32_b20", "ms_sub64_b20", "ms_nosub32_b20", "ms_nosub64_b20", "ndim_all32_b20", "ndim_all64_b20", "ndim_gauss_all32",
              "ndim_vec32_b20", "ndim_vec64_b20"]
+
+# configurations eligible for lane-split walkers, with the lane count placement 3 gives them
+LANE_SPLIT = {"ndim_all16": 2, "ndim_all32_b20": 2, "ndim_all64_b20": 4, "lanes_all128_auto": 8, "lanes_all192": 8}
 
 CALLBACK_RUNS = ["c1_simple_short", "vec_exp4", "ms_sub16", "auto_default", "ut2_irange", "nopdf_box", "gauss_vec6_v3"]
 

@@ -127,12 +127,14 @@ def test_all_move_footprint_and_unrolling_rules(mcig, monkeypatch):
     coordinates are fully unrolled (the engine prepends MCIG_UNROLL_MAX 256 unless the experiment knob names it)."""
     import re
 
-    def make(ndim, pdf=None):
+    def make(ndim, pdf=None, placement=1):
         mci = mcig.MCI(ndim)
         mci.setRngMode(0)
         mci.setNWalkers(4096)
         mci.addSamplingFunction((pdf or mcig.ExpNDPDF)(ndim))
         mci.addObservable(mcig.XND(ndim), 20, 1)
+        if placement is not None:
+            mci.setStatePlacement(placement)
         mci.prebuild()
         return mci.kernelSource()
 
@@ -145,8 +147,15 @@ def test_all_move_footprint_and_unrolling_rules(mcig, monkeypatch):
     off = make(64)
     assert "MS_MAIN_VPO = false" in off and block(on) == 2*block(off)
     monkeypatch.delenv("MCIG_ALL_VPO")
-    assert "MS_MAIN_VPO = false" in make(8)  # register-resident walkers keep their proto values in registers
+    assert "MS_MAIN_VPO = false" in make(8, placement=None)  # register-resident walkers keep their proto values in registers
+    # automatic placement: eligible all-moves (uniform proposal, SUM_ACCEPTANCE sampling function, element-wise observables) spread one
+    # walker over several lanes from 64 coordinates on; below, and for ineligible configurations, the rules above apply
+    auto64 = make(64, placement=None)
+    assert "walk_kernel_lanes" in auto64 and "LANES = 4, NL = 16" in auto64
+    assert "LANES = 8, NL = 16" in make(128, placement=None) and "LANES = 16, NL = 16" in make(256, placement=None)
+    assert "walk_kernel_smem" in make(32, placement=None)
+    assert "LANES = 2, NL = 16" in make(32, placement=3)
     assert "#define MCIG_UNROLL_MAX 256" in make(96)
-    assert "#define MCIG_UNROLL_MAX" not in make(320)
+    assert "#define MCIG_UNROLL_MAX" not in make(320, placement=2)
     monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_UNROLL_MAX=16")
     assert make(96).count("#define MCIG_UNROLL_MAX") == 1

@@ -135,7 +135,7 @@ def test_all_move_proto_views_equal_proto_arrays(case, mcig, monkeypatch):
     res = {}
     for flag in ("1", "0"):
         monkeypatch.setenv("MCIG_ALL_VPO", flag)
-        mci = build_mci(mcig, spec, nwalkers=1024, mode=0)
+        mci = build_mci(mcig, spec, nwalkers=1024, mode=0, placement=1)  # (the automatic choice at ndim 96 would be lane-split walkers)
         assert ("MS_MAIN_VPO = " + ("true" if flag == "1" else "false")) in mci.kernelSource()
         avg, err = mci.integrate(spec["nmc"], False, False)
         wavg, _ = mci.walkerResults()

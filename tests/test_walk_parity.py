@@ -83,6 +83,44 @@ def test_c3_shapes_replay_on_every_placement(name, placement, mcig, oracle, gold
     assert _close(err, ref["err"], ERR_RTOL, atol=1e-18)
 
 
+@pytest.mark.parametrize("name", sorted(configs.LANE_SPLIT))
+def test_lane_split_walkers_replay_bit_exact(name, mcig, oracle, golden_runs):
+    """State placement 3: one walker spread over several lanes of a warp (all-moves over many coordinates, src of the move:
+    include/mci/SRRDAllMove.hpp:67-80). In replay mode the two sums of the acceptance exp(sum po - sum pn) (test/common/TestMCIFunctions.hpp:
+    173-177, 240-245) travel through the lanes in coordinate order, so every accept decision, the trajectory and the calibrated step sizes are
+    the reference's bit for bit; the accumulators are per coordinate and keep the reference's order."""
+    spec = configs.RUNS[name]
+    g = golden_runs[name]
+    mci = build_mci(mcig, spec, placement=3)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    src = mci.kernelSource()
+    assert "walk_kernel_lanes" in src and "LANES = %d" % configs.LANE_SPLIT[name] in src
+    assert mci.getAcceptanceRate() == float.fromhex(g["acc_rate"])
+    assert list(mci.getX()) == fromhex(g["x_final"]), "final position not bit-exact"
+    nt = max(1, spec.get("ntypes", 1))
+    assert [mci.getMRT2Step(i) for i in range(nt)] == fromhex(g["steps_final"])
+    assert _close(avg, fromhex(g["avg"]), AVG_RTOL), np.max(np.abs(avg - np.array(fromhex(g["avg"]))))
+    assert _close(err, fromhex(g["err"]), ERR_RTOL, atol=1e-18)
+
+
+@pytest.mark.parametrize("name", ["ndim_all64_b20", "lanes_all128_auto"])
+def test_lane_split_walkers_philox_equal_shared_memory_walkers(name, mcig):
+    """Production mode: the lanes draw from the same (group, walker, block) -> word mapping as every other placement, so a lane-split walker
+    follows the same chain as its shared-memory twin; only the association of the log-acceptance sum differs (butterfly over the lanes), which
+    can flip a decision only when the uniform lies within an ulp of the acceptance."""
+    spec = dict(configs.RUNS[name], do_find=False, do_decorr=False)
+    out = []
+    for placement in (1, 3):
+        mci = build_mci(mcig, spec, nwalkers=192, mode=0, placement=placement)
+        avg, err = mci.integrate(1000, False, False)
+        out.append((avg.copy(), err.copy(), mci.getAcceptanceRate(), np.array([mci.getX(walker=w) for w in (0, 100, 191)])))
+    assert out[0][2] == out[1][2], "accept counts differ"
+    assert np.array_equal(out[0][3], out[1][3]), "positions differ"
+    scale = max(1.0, float(np.max(np.abs(out[0][0]))))
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-12*scale
+    assert np.allclose(out[0][1], out[1][1], rtol=1e-9, atol=1e-15)
+
+
 @pytest.mark.parametrize("name", configs.C3_SHAPES)
 def test_c3_shapes_philox_placements_agree(name, mcig):
     """Production (Philox) kernels of the same shapes: the shared- and global-memory placements run the same code over different views
@@ -91,7 +129,7 @@ def test_c3_shapes_philox_placements_agree(name, mcig):
     spec = configs.RUNS[name]
     n = min(spec["nmc"], 2000)
     out = []
-    for placement in (0, 1, 2):
+    for placement in (0, 1, 2):  # (lane-split walkers, which the automatic choice would pick for some of these shapes: tests above)
         mci = build_mci(mcig, spec, nwalkers=160, mode=0, placement=placement)
         mci.setLazyAccumulation(0)
         avg, err = mci.integrate(n, False, False)

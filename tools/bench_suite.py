@@ -13,9 +13,11 @@ import mcintegratorplusplus_b200 as m  # noqa: E402
 HBM_GBS = 6550.7  # MEASURED_PEAKS.json (driver-measured copy bandwidth on this pool)
 
 
-def c3_ndim(move, ndims=(1, 2, 4, 8, 16, 32, 64), W=65536, nmc=20000):
+def c3_ndim(move, ndims=(1, 2, 4, 8, 16, 32, 64), W=65536, nmc=20000, placement=None):
     for nd in ndims:
         mci = m.MCI(nd)
+        if placement is not None:
+            mci.setStatePlacement(placement)
         mci.setRngMode(0)
         mci.setSeed(1337)
         mci.setNWalkers(W)
@@ -34,7 +36,7 @@ def c3_ndim(move, ndims=(1, 2, 4, 8, 16, 32, 64), W=65536, nmc=20000):
         avg, err = mci.integrate(nmc, False, False)
         wall = time.perf_counter() - t0
         t = mci.timings()
-        print(json.dumps({"config": "C3_ndim_" + move, "ndim": nd, "walkers": W, "nmc": nmc, "steps_per_s": W*nmc/(t["walk_ms"]*1e-3),
+        print(json.dumps({"config": "C3_ndim_" + move, "placement": placement, "ndim": nd, "walkers": W, "nmc": nmc, "steps_per_s": W*nmc/(t["walk_ms"]*1e-3),
                           "walk_ms": t["walk_ms"], "estim_ms": t["estim_ms"], "wall_ms": 1e3*wall, "acceptance": mci.getAcceptanceRate(),
                           "max_abs_avg": float(np.max(np.abs(avg))), "max_err": float(np.max(err))}), flush=True)
 
@@ -121,6 +123,9 @@ if __name__ == "__main__":
         c3_ndim("vec", ndims=(128, 256, 512, 1024), W=16384, nmc=20000)
         c3_ndim("all", ndims=(128, 256, 512, 1024), W=16384, nmc=2000)
         c3_ndim("multistep", ndims=(64, 128, 256), W=16384, nmc=200)
+    if "c3lanes" in which:  # lane-split walkers (placement 3) against the shared-memory placement
+        for pl in (1, 3):
+            c3_ndim("all", ndims=(32, 48, 64, 96, 128, 256), W=65536, nmc=2000, placement=pl)
     if "c4" in which:
         c4_estimators()
     if "c5" in which:
