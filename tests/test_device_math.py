@@ -30,6 +30,31 @@ def test_philox_known_answers(mcig):
     assert np.array_equal(data, want)
 
 
+def test_fp64_pipe_mulhi_equals_the_integer_multiplier(mcig):
+    """mulhi_f64<M>(a) (one DFMA rounding towards zero on 2^52 + a) is floor(a M / 2^32) for every word: edge values and a pseudo-random sweep
+    against __umulhi, both Philox multipliers. (The walk loop keeps the integer multiplier: profiles/r02_f64hi_knobs.log; MCIG_F64HI0/1 switch rounds over.)"""
+    src = """struct MulhiCheck { static constexpr int NPAR = 0; const double * par;
+      template <class X, class O> __device__ void observableFunction(const X & in, O & out) const {
+        const unsigned edge[8] = {0u, 1u, 2u, 0x7fffffffu, 0x80000000u, 0xfffffffeu, 0xffffffffu, 0x00010000u};
+        unsigned bad = 0, a = (unsigned)__double2loint(in[0]*1e6) ^ 0x9e3779b9u;
+        for (int i = 0; i < 4096; ++i) {
+          const unsigned v = (i < 8) ? edge[i] : a;
+          bad += (mcig::mulhi_f64<0xD2511F53u>(v) != __umulhi(0xD2511F53u, v)) + (mcig::mulhi_f64<0xCD9E8D57u>(v) != __umulhi(0xCD9E8D57u, v));
+          a = a*1664525u + 1013904223u;
+        }
+        out[0] = (double)bad; out[1] = (double)mcig::mulhi_f64<0xD2511F53u>(0xffffffffu); } };"""
+    mcig.register_plugin(1, "MulhiCheck", "MulhiCheck", src, ndim=1, nvalues=2)
+    mci = mcig.MCI(1)
+    mci.setRngMode(0)
+    mci.setNWalkers(64)
+    mci.addSamplingFunction(mcig.Exp1DPDF())
+    mci.addObservable(mcig.Observable("MulhiCheck"), 1, 1, False, mcig.EstimatorType.Noop)
+    mci.integrate(16, False, False)
+    for w in (0, 31, 63):
+        d = mci.obsData(0, walker=w, nobs=2)
+        assert (d[:, 0] == 0).all() and (d[:, 1] == float((0xffffffff*0xD2511F53) >> 32)).all()
+
+
 def test_exp_bit_equal_to_libdevice(mcig):
     src = """struct ExpCheck { static constexpr int NPAR = 0; const double * par;
       template <class X, class O> __device__ void observableFunction(const X & in, O & out) const {
