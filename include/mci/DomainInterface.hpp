@@ -5,6 +5,7 @@
 #define MCIG_MCI_DOMAININTERFACE_HPP
 
 #include "mci/Clonable.hpp"
+#include "mci/DeviceFunctor.hpp"
 
 #include <algorithm>
 #include <limits>
@@ -36,8 +37,16 @@ public:
         std::fill(centerX, centerX + ndim, 0.5);
         this->scaleToDomain(centerX);
     }
-    virtual bool isPeriodic() const = 0; // engine hook: false = unbound
-    virtual void getBounds(double lbounds[], double ubounds[]) const = 0;
+    // engine hooks. The two built-in domains are recognised by isPeriodic / getBounds. A user-defined domain (the reference's DomainInterface is
+    // user-subclassable, include/mci/DomainInterface.hpp:26-55) implements the reference's five methods below for the host side and returns the
+    // device twin of applyDomain / scaleToDomain from deviceFunctor() (plugin kind MCIG_PLUGIN_DOMAIN: wrap(i, x), scale(i, u01); include/mcig.h)
+    virtual bool isPeriodic() const { return false; }
+    virtual void getBounds(double lbounds[], double ubounds[]) const
+    {
+        std::fill(lbounds, lbounds + ndim, -domain_conv::infinity);
+        std::fill(ubounds, ubounds + ndim, domain_conv::infinity);
+    }
+    virtual DeviceFunctor deviceFunctor() const { return DeviceFunctor(); }
     virtual void applyDomain(double x[]) const = 0;
     virtual void scaleToDomain(double normX[]) const = 0;
     virtual void getSizes(double dimSizes[]) const = 0;

@@ -65,21 +65,14 @@ private:
 
     void pushConfiguration()
     {
-        if (_dirtyDomain) {
-            if (_domain->isPeriodic()) {
-                std::vector<double> lb(static_cast<size_t>(_ndim)), ub(static_cast<size_t>(_ndim));
-                _domain->getBounds(lb.data(), ub.data());
-                detail::check(mcig_set_domain_ortho(_ctx, lb.data(), ub.data()));
-            }
-            else { detail::check(mcig_set_domain_unbound(_ctx)); }
-            _dirtyDomain = false;
-        }
+        pushDomainOnly();
         if (_dirtyMove) {
             const TrialMoveInterface & m = *_trialMove;
             int mt = MCIG_MOVE_ALL;
             if (m.getMoveType() == MoveType::Vec) { mt = MCIG_MOVE_VEC; }
             if (m.getMoveType() == MoveType::MultiStep) { mt = MCIG_MOVE_MULTISTEP; }
             detail::check(mcig_set_move(_ctx, mt, toSrrd(m.getSRRDType()), m.getVecLen(), m.getNTypes(), m.getNTypes() > 1 ? m.getTypeEnds() : nullptr));
+            if (!m.getSRRDParams().empty()) { detail::check(mcig_set_srrd_params(_ctx, static_cast<int>(m.getSRRDParams().size()), m.getSRRDParams().data())); }
             if (mt == MCIG_MOVE_MULTISTEP) {
                 const auto & ms = dynamic_cast<const MultiStepMove &>(m);
                 detail::check(mcig_multistep_config(_ctx, ms.getNSteps()));
@@ -154,6 +147,12 @@ public:
     void setX(const double x[])
     {
         pushDomainOnly();
+        if (!_domain->deviceFunctor().name.empty()) { // user-defined domain: applied here, by its host twin (src/MCIntegrator.cpp:600-604)
+            std::vector<double> t(x, x + _ndim);
+            _domain->applyDomain(t.data());
+            detail::check(mcig_set_x(_ctx, t.data()));
+            return;
+        }
         detail::check(mcig_set_x(_ctx, x));
     }
     void moveX()
@@ -384,7 +383,16 @@ private:
     void pushDomainOnly()
     {
         if (!_dirtyDomain) { return; }
-        if (_domain->isPeriodic()) {
+        const DeviceFunctor df = _domain->deviceFunctor();
+        if (!df.name.empty()) { // a user-defined domain: its device functor, plus getSizes / getVolume for the host-side rules
+            std::vector<double> sizes(static_cast<size_t>(_ndim)), x(static_cast<size_t>(_ndim));
+            _domain->getSizes(sizes.data());
+            detail::check(mcig_get_x(_ctx, 0, x.data()));
+            detail::check(mcig_set_domain_plugin(_ctx, df.resolve(MCIG_PLUGIN_DOMAIN, _ndim, 0), df.params.data(), static_cast<int>(df.params.size()), sizes.data(), _domain->getVolume()));
+            _domain->applyDomain(x.data()); // (the engine applies its built-in domains to the position itself)
+            detail::check(mcig_set_x(_ctx, x.data()));
+        }
+        else if (_domain->isPeriodic()) {
             std::vector<double> lb(static_cast<size_t>(_ndim)), ub(static_cast<size_t>(_ndim));
             _domain->getBounds(lb.data(), ub.data());
             detail::check(mcig_set_domain_ortho(_ctx, lb.data(), ub.data()));

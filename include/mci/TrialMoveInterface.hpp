@@ -11,7 +11,9 @@
 
 #include <algorithm>
 #include <memory>
+#include <random>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace mci
@@ -31,6 +33,11 @@ public:
     bool hasStepSizes() const { return this->getNStepSizes() > 0; }
     virtual MoveType getMoveType() const = 0;
     virtual SRRDType getSRRDType() const { return SRRDType::Uniform; }
+    virtual const std::vector<double> & getSRRDParams() const // parameters of a pre-made distribution passed to the constructor; empty = defaults
+    {
+        static const std::vector<double> none;
+        return none;
+    }
     virtual int getVecLen() const { return 1; }
     virtual int getNTypes() const = 0;
     virtual const int * getTypeEnds() const = 0;
@@ -54,6 +61,7 @@ protected:
     std::vector<int> _typeEnds;
     std::vector<double> _stepSizes;
     const SRRDType _srrd;
+    std::vector<double> _srrdPar; // see mcig_set_srrd_params (include/mcig.h)
     TypedMoveInterface(int ndim, int ntypes, const int typeEnds[], double initStepSize, SRRDType srrd):
             TrialMoveInterface(ndim), _ntypes(ntypes), _srrd(srrd)
     {
@@ -68,6 +76,7 @@ protected:
 
 public:
     SRRDType getSRRDType() const final { return _srrd; }
+    const std::vector<double> & getSRRDParams() const final { return _srrdPar; }
     int getNTypes() const final { return _ntypes; }
     const int * getTypeEnds() const final { return _typeEnds.data(); }
     int getNStepSizes() const final { return _ntypes; }
@@ -82,12 +91,92 @@ public:
     }
 };
 
+// Symmetrised positive distribution (include/mci/TrialMoveInterface.hpp:81-98): value from prrd, sign from a fair coin. Kept so that user code
+// building SymmetrizedPRRD<std::gamma_distribution<double>> objects for a move constructor compiles unchanged; the device engine reads its parameters.
+template <class PRRD>
+struct SymmetrizedPRRD
+{
+private:
+    std::bernoulli_distribution bd;
+
+public:
+    PRRD prrd;
+    SymmetrizedPRRD() = default;
+    explicit SymmetrizedPRRD(PRRD myPRRD) { prrd = myPRRD; }
+    double operator()(std::mt19937_64 &rgen)
+    {
+        const double val = prrd(rgen);
+        return (bd(rgen)) ? val : -val;
+    }
+};
+
+// The reference's move types are templates over the distribution TYPE and take an optional pre-made distribution OBJECT (`const SRRD * rdist`,
+// include/mci/SRRDAllMove.hpp:45-58). Here the distribution is a tag plus parameters handed to the kernel generator: SRRDDist maps each tag to the
+// reference's distribution type and reads the parameters out of such an object. Locations must be 0 (a move distribution has to be symmetric).
+namespace detail
+{
+inline void requireSymmetric(bool ok, const char * what)
+{
+    if (!ok) { throw std::invalid_argument(std::string("[mcig] ") + what + ": the device engine takes move distributions that are symmetric around 0"); }
+}
+inline void checkUniformRdist(const std::uniform_real_distribution<double> * rdist)
+{
+    if (rdist != nullptr && !(rdist->a() == -1. && rdist->b() == 1.)) {
+        throw std::invalid_argument("[mcig] uniform move distributions other than (-1, 1) are expressed through the step size");
+    }
+}
+} // namespace detail
+template <SRRDType T> struct SRRDDist;
+template <> struct SRRDDist<SRRDType::Gaussian> {
+    typedef std::normal_distribution<double> type;
+    static std::vector<double> params(const type &d) { detail::requireSymmetric(d.mean() == 0., "normal_distribution with a mean"); return {d.stddev()}; }
+};
+template <> struct SRRDDist<SRRDType::Student> {
+    typedef std::student_t_distribution<double> type;
+    static std::vector<double> params(const type &d) { return {d.n()}; }
+};
+template <> struct SRRDDist<SRRDType::Cauchy> {
+    typedef std::cauchy_distribution<double> type;
+    static std::vector<double> params(const type &d) { detail::requireSymmetric(d.a() == 0., "cauchy_distribution with a location"); return {d.b()}; }
+};
+template <> struct SRRDDist<SRRDType::Exponential> {
+    typedef SymmetrizedPRRD<std::exponential_distribution<double>> type;
+    static std::vector<double> params(const type &d) { return {d.prrd.lambda()}; }
+};
+template <> struct SRRDDist<SRRDType::Gamma> {
+    typedef SymmetrizedPRRD<std::gamma_distribution<double>> type;
+    static std::vector<double> params(const type &d) { return {d.prrd.alpha(), d.prrd.beta()}; }
+};
+template <> struct SRRDDist<SRRDType::Weibull> {
+    typedef SymmetrizedPRRD<std::weibull_distribution<double>> type;
+    static std::vector<double> params(const type &d) { return {d.prrd.a(), d.prrd.b()}; }
+};
+template <> struct SRRDDist<SRRDType::Lognormal> {
+    typedef SymmetrizedPRRD<std::lognormal_distribution<double>> type;
+    static std::vector<double> params(const type &d) { return {d.prrd.m(), d.prrd.s()}; }
+};
+template <> struct SRRDDist<SRRDType::Chisq> {
+    typedef SymmetrizedPRRD<std::chi_squared_distribution<double>> type;
+    static std::vector<double> params(const type &d) { return {d.prrd.n()}; }
+};
+template <> struct SRRDDist<SRRDType::Fisher> {
+    typedef SymmetrizedPRRD<std::fisher_f_distribution<double>> type;
+    static std::vector<double> params(const type &d) { return {d.prrd.m(), d.prrd.n()}; }
+};
+
 // all-particle move with a symmetric real-valued random distribution (include/mci/SRRDAllMove.hpp)
 class SRRDAllMove: public TypedMoveInterface
 {
     TrialMoveInterface * _clone() const final { return new SRRDAllMove(*this); }
 
+protected:
+    void setSRRDParams(std::vector<double> par) { _srrdPar = std::move(par); }
+
 public:
+    // UniformAllMove(ndim, step, &uniform_real_distribution(-1, 1)): the reference's uniform instantiation with its optional pre-made distribution
+    SRRDAllMove(int ndim, int ntypes, const int typeEnds[], double initStepSize, const std::uniform_real_distribution<double> * rdist):
+            SRRDAllMove(ndim, ntypes, typeEnds, initStepSize, SRRDType::Uniform) { detail::checkUniformRdist(rdist); }
+    SRRDAllMove(int ndim, double initStepSize, const std::uniform_real_distribution<double> * rdist): SRRDAllMove(ndim, 1, nullptr, initStepSize, rdist) {}
     SRRDAllMove(int ndim, int ntypes, const int typeEnds[], double initStepSize, SRRDType srrd = SRRDType::Uniform):
             TypedMoveInterface(ndim, ntypes, typeEnds, initStepSize, srrd) {}
     SRRDAllMove(int ndim, double initStepSize, SRRDType srrd = SRRDType::Uniform): SRRDAllMove(ndim, 1, nullptr, initStepSize, srrd) {}
@@ -99,9 +188,25 @@ public:
 class SRRDVecMove: public TypedMoveInterface
 {
     const int _nvecs, _veclen;
-    TrialMoveInterface * _clone() const final { return new SRRDVecMove(*this); }
+    // The reference's vec-move clone does not pass its distribution on (include/mci/SRRDVecMove.hpp:30-33: `new SRRDVecMove(_nvecs, _veclen, _ntypes,
+    // _typeEnds, _stepSizes)`, unlike SRRDAllMove.hpp:34-37), and MCI::setTrialMove(const TrialMoveInterface &) stores a clone: a pre-made distribution
+    // handed to a VEC move never reaches the sampling loop there -- the default-constructed one is used. Mirrored, so that the same program gives the
+    // same numbers (pinned by the par_*_vec goldens, tests/configs.py); mcig_set_srrd_params itself works for vec-moves too.
+    TrialMoveInterface * _clone() const final
+    {
+        SRRDVecMove * c = new SRRDVecMove(*this);
+        c->_srrdPar.clear();
+        return c;
+    }
+
+protected:
+    void setSRRDParams(std::vector<double> par) { _srrdPar = std::move(par); }
 
 public:
+    SRRDVecMove(int nvecs, int veclen, int ntypes, const int typeEnds[], double initStepSize, const std::uniform_real_distribution<double> * rdist):
+            SRRDVecMove(nvecs, veclen, ntypes, typeEnds, initStepSize, SRRDType::Uniform) { detail::checkUniformRdist(rdist); }
+    SRRDVecMove(int nvecs, int veclen, double initStepSize, const std::uniform_real_distribution<double> * rdist):
+            SRRDVecMove(nvecs, veclen, 1, nullptr, initStepSize, rdist) {}
     SRRDVecMove(int nvecs, int veclen, int ntypes, const int typeEnds[], double initStepSize, SRRDType srrd = SRRDType::Uniform):
             TypedMoveInterface(nvecs*veclen, ntypes, typeEnds, initStepSize, srrd), _nvecs(nvecs), _veclen(veclen)
     {
@@ -125,17 +230,27 @@ using UniformAllMove = SRRDAllMove;
 using UniformVecMove = SRRDVecMove;
 
 // the other named instantiations (include/mci/SRRDAllMove.hpp:85-95, SRRDVecMove.hpp:101-111): same constructors, distribution fixed by the type
+// and the optional pre-made distribution (e.g. StudentAllMove(ndim, 0.05, &student_t(2)), test/ut5/main.cpp:110-113)
 template <SRRDType T>
 struct SRRDAllMoveOf final: public SRRDAllMove
 {
-    SRRDAllMoveOf(int ndim, double initStepSize): SRRDAllMove(ndim, initStepSize, T) {}
-    SRRDAllMoveOf(int ndim, int ntypes, const int typeEnds[], double initStepSize): SRRDAllMove(ndim, ntypes, typeEnds, initStepSize, T) {}
+    typedef typename SRRDDist<T>::type Dist;
+    SRRDAllMoveOf(int ndim, double initStepSize, const Dist * rdist = nullptr): SRRDAllMoveOf(ndim, 1, nullptr, initStepSize, rdist) {}
+    SRRDAllMoveOf(int ndim, int ntypes, const int typeEnds[], double initStepSize, const Dist * rdist = nullptr): SRRDAllMove(ndim, ntypes, typeEnds, initStepSize, T)
+    {
+        if (rdist != nullptr) { this->setSRRDParams(SRRDDist<T>::params(*rdist)); }
+    }
 };
 template <SRRDType T>
 struct SRRDVecMoveOf final: public SRRDVecMove
 {
-    SRRDVecMoveOf(int nvecs, int veclen, double initStepSize): SRRDVecMove(nvecs, veclen, initStepSize, T) {}
-    SRRDVecMoveOf(int nvecs, int veclen, int ntypes, const int typeEnds[], double initStepSize): SRRDVecMove(nvecs, veclen, ntypes, typeEnds, initStepSize, T) {}
+    typedef typename SRRDDist<T>::type Dist;
+    SRRDVecMoveOf(int nvecs, int veclen, double initStepSize, const Dist * rdist = nullptr): SRRDVecMoveOf(nvecs, veclen, 1, nullptr, initStepSize, rdist) {}
+    SRRDVecMoveOf(int nvecs, int veclen, int ntypes, const int typeEnds[], double initStepSize, const Dist * rdist = nullptr):
+            SRRDVecMove(nvecs, veclen, ntypes, typeEnds, initStepSize, T)
+    {
+        if (rdist != nullptr) { this->setSRRDParams(SRRDDist<T>::params(*rdist)); }
+    }
 };
 using GaussianAllMove = SRRDAllMoveOf<SRRDType::Gaussian>;
 using StudentAllMove = SRRDAllMoveOf<SRRDType::Student>;

@@ -47,7 +47,7 @@ enum {
     MCIG_RNG_REPLAY = 2    /* per-walker std::mt19937_64 + libstdc++ distributions generated on the host and consumed by
                               the kernel in the reference's order: bit-exact reference trajectories (parity mode) */
 };
-enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1, MCIG_PLUGIN_CALLBACK = 2 };
+enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1, MCIG_PLUGIN_CALLBACK = 2, MCIG_PLUGIN_DOMAIN = 3 };
 /* plugin flags (sampling functions) */
 enum {
     MCIG_PLUGIN_HAS_UPDATE = 1,     /* functor overrides updatedAcceptance (selective update for single-vector moves) */
@@ -106,12 +106,29 @@ int mcig_get_x(mcig_ctx * ctx, int64_t walker, double * x /*[ndim]*/);
 /* ---- domain: MCI::resetDomain / setIRange  src/MCIntegrator.cpp:390-408 */
 int mcig_set_domain_unbound(mcig_ctx * ctx);
 int mcig_set_domain_ortho(mcig_ctx * ctx, const double * lbounds, const double * ubounds);
+/* MCI::setDomain(const DomainInterface &) with a user-defined domain (the reference's DomainInterface is user-subclassable,
+ * include/mci/DomainInterface.hpp:26-55): a device functor of plugin kind MCIG_PLUGIN_DOMAIN,
+ *     struct MyDomain { static constexpr int NPAR = ...; const double * par;
+ *         __device__ void wrap(int i, double & xi) const;        // applyDomain, coordinate by coordinate
+ *         __device__ double scale(int i, double u01) const; };   // scaleToDomain, coordinate by coordinate
+ * plus what the host needs from getSizes / getVolume: the lengths of the ndim dimensions (infinite: 2 x float max; they cap the calibrated
+ * step sizes, src/MCIntegrator.cpp:151-155) and the volume (0 = infinite; plain sampling without a sampling function needs a finite one).
+ * Separable domains only: coordinate i is mapped knowing only coordinate i (reflecting walls, per-coordinate periods, ...). Positions handed
+ * to mcig_set_x* are taken as given: the caller applies the domain (the C++ facade calls the host class's applyDomain). */
+int mcig_set_domain_plugin(mcig_ctx * ctx, int plugin_id, const double * par, int npar, const double * dim_sizes /*[ndim]*/, double volume);
 
 /* ---- trial move: MCI::setTrialMove(MoveType) / (SRRDType, veclen, ntypes, typeEnds)  src/MCIntegrator.cpp:423-446.
  *      Step sizes are reset to DEFAULT_MRT2STEP = 0.05 (Factories.hpp:145). MultiStep: sub-move = uniform single-vector
  *      move of length veclen, nsteps <= 0 means ndim (MultiStepMove.hpp:46-52); its own sampling functions are added
  *      with mcig_multistep_add_pdf (MultiStepMove::addSamplingFunction). */
 int mcig_set_move(mcig_ctx * ctx, int move_type, int srrd, int veclen, int ntypes, const int * type_ends);
+/* A move built around a pre-made distribution instead of createSymRRD<>()'s default (the `const SRRD * rdist` argument of the reference's move
+ * constructors, include/mci/SRRDAllMove.hpp:45-58, SRRDVecMove.hpp:41-68; test/ut5/main.cpp:110-113 passes student_t(2)). Call after mcig_set_move
+ * (which resets to the defaults). par: Gaussian {stddev}; Student {n}; Cauchy {b}; Exponential {lambda}; Gamma {alpha, beta}; Weibull {a, b};
+ * Lognormal {m, s}; Chisq {n}; Fisher {m, n}; npar = 0 restores the defaults. Locations stay 0 (a move distribution must be symmetric).
+ * Replay mode consumes the libstdc++ outputs of exactly that distribution; the Philox modes sample the same law from a fixed number of uniforms
+ * per value, which for Gamma / Chisq / Fisher needs shapes that are multiples of 1/2 (refused with MCIG_ERR_INVALID_ARGUMENT otherwise). */
+int mcig_set_srrd_params(mcig_ctx * ctx, int npar, const double * par);
 int mcig_multistep_config(mcig_ctx * ctx, int nsteps);
 int mcig_multistep_add_pdf(mcig_ctx * ctx, int plugin_id, const double * par, int npar);
 /* MCI::setMRT2Step / getMRT2Step  src/MCIntegrator.cpp:557-585 */

@@ -37,7 +37,9 @@ SIGNATURES = {
     "mcig_get_x": (C.c_int, [_ctx, C.c_int64, _dp]),
     "mcig_set_domain_unbound": (C.c_int, [_ctx]),
     "mcig_set_domain_ortho": (C.c_int, [_ctx, _dp, _dp]),
+    "mcig_set_domain_plugin": (C.c_int, [_ctx, C.c_int, _dp, C.c_int, _dp, C.c_double]),
     "mcig_set_move": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
+    "mcig_set_srrd_params": (C.c_int, [_ctx, C.c_int, _dp]),
     "mcig_multistep_config": (C.c_int, [_ctx, C.c_int]),
     "mcig_multistep_add_pdf": (C.c_int, [_ctx, C.c_int, _dp, C.c_int]),
     "mcig_get_nsteps_sizes": (C.c_int, [_ctx]),

@@ -87,6 +87,11 @@ class StepCallback(Plugin):
     kind = 2
 
 
+class Domain(Plugin):
+    """A user-defined (separable) domain as a device functor (see include/mcig.h: mcig_set_domain_plugin)."""
+    kind = 3
+
+
 def register_plugin(kind, name, type_expr, source, ndim=0, nvalues=0, npar=0, has_update=False, elementwise=False, log_acceptance=False,
                     dependent=False, proto_element=False, sum_acceptance=False):
     """Register a user functor (CUDA C++ source, see csrc/device/mcig_functors.cuh for the contract).
@@ -213,6 +218,13 @@ class MCI:
     # --- domain (include/mci/MCIntegrator.hpp:129-137)
     def resetDomain(self): _capi.check(self._lib.mcig_set_domain_unbound(self._ctx))
 
+    def setDomain(self, domain, sizes, volume):
+        """setDomain(Domain functor, lengths of the ndim dimensions, volume (0 = infinite)): MCI::setDomain with a user-defined DomainInterface"""
+        a, p = _darr(domain.par)
+        sz = np.full(self._ndim, sizes, dtype=np.float64) if np.isscalar(sizes) else np.asarray(sizes, dtype=np.float64)
+        b, pb = _darr(sz)
+        _capi.check(self._lib.mcig_set_domain_plugin(self._ctx, domain.plugin_id(), p, len(domain.par), pb, float(volume)))
+
     def setIRange(self, lbound, ubound):
         lb = np.full(self._ndim, lbound, dtype=np.float64) if np.isscalar(lbound) else np.asarray(lbound, dtype=np.float64)
         ub = np.full(self._ndim, ubound, dtype=np.float64) if np.isscalar(ubound) else np.asarray(ubound, dtype=np.float64)
@@ -221,9 +233,11 @@ class MCI:
         _capi.check(self._lib.mcig_set_domain_ortho(self._ctx, pa, pb))
 
     # --- trial moves (include/mci/MCIntegrator.hpp:139-146)
-    def setTrialMove(self, move, veclen=0, ntypes=1, typeEnds=None, nsteps=0, sub_pdfs=()):
+    def setTrialMove(self, move, veclen=0, ntypes=1, typeEnds=None, nsteps=0, sub_pdfs=(), params=None):
         """setTrialMove(MoveType) or setTrialMove(SRRDType, veclen, ntypes, typeEnds). For MoveType.MultiStep, `nsteps` and
-        `sub_pdfs` configure the move's own sub-sampling (MultiStepMove::setNSteps / addSamplingFunction)."""
+        `sub_pdfs` configure the move's own sub-sampling (MultiStepMove::setNSteps / addSamplingFunction). `params`: the parameters of a
+        pre-made distribution handed to the move (reference: the `rdist` constructor argument, include/mci/SRRDAllMove.hpp:45-58), e.g.
+        setTrialMove(SRRDType.Student, 0, params=(2.0,)) for test/ut5's StudentAllMove(ndim, 0.05, &student_t(2))."""
         te = None
         if typeEnds is not None:
             te_arr = np.ascontiguousarray(typeEnds, dtype=np.int32)
@@ -237,6 +251,9 @@ class MCI:
             vl = max(1, veclen)
             srrd = int(move)
         _capi.check(self._lib.mcig_set_move(self._ctx, mt, srrd, vl, ntypes, te))
+        if params is not None and len(params) > 0:
+            a, p = _darr(list(params))
+            _capi.check(self._lib.mcig_set_srrd_params(self._ctx, len(params), p))
         if mt == int(MoveType.MultiStep):
             _capi.check(self._lib.mcig_multistep_config(self._ctx, int(nsteps)))
             for pdf in sub_pdfs:

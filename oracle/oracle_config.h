@@ -100,6 +100,11 @@ typedef struct {
     /* emulate R independent MPI ranks (seed r = seeds[r]) combined as src/MPIMCI.cpp:85-92; 0/1 = single chain.
        nranks_for_minstat enters MIN_STAT/MIN_NMC (src/MCIntegrator.cpp:107,193) */
     int32_t nranks_for_minstat;
+    /* parameters of the move's distribution (a pre-made distribution passed to the move's constructor, include/mci/SRRDAllMove.hpp:45-58,
+       test/ut5/main.cpp:110-113); 0 = createSymRRD<>() defaults. Gaussian: stddev; Student: n; Cauchy: b; Exponential: lambda; Gamma: alpha, beta;
+       Weibull: a, b; Lognormal: m, s; Chisq: n; Fisher: m, n. Reference harness only (the C restatement covers the default distributions). */
+    int32_t srrd_npar;
+    double srrd_par[2];
 } orc_config_t;
 
 typedef struct {

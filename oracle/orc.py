@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("ub", C.c_double * MAXDIM), ("x0", C.c_double * MAXDIM), ("nobs", C.c_int32), ("obs", Obs * MAXOBS),
         ("nfind", C.c_int32), ("ndecorr", C.c_int64), ("target_acc", C.c_double), ("nmc", C.c_int64),
         ("do_find", C.c_int32), ("do_decorr", C.c_int32), ("nranks_for_minstat", C.c_int32),
+        ("srrd_npar", C.c_int32), ("srrd_par", C.c_double * 2),
     ]
 
 
@@ -65,7 +66,7 @@ def default_estim(blocksize, flag_correlated=None):
 
 def make_config(ndim, seed, pdf_id, obs, nmc, *, move_type=MOVE_ALL, srrd=SRRD_UNIFORM, veclen=0, ntypes=1, type_ends=None,
                 steps=(0.05,), ms_nsteps=0, ms_sub_pdf_id=PDF_NONE, lb=None, ub=None, x0=None, nfind=-50, ndecorr=-10000,
-                target_acc=0.5, do_find=False, do_decorr=False, nranks=1):
+                target_acc=0.5, do_find=False, do_decorr=False, nranks=1, srrd_par=()):
     """obs: list of (obs_id, blocksize, nskip[, flag_equil[, estim_type]]) tuples (defaults as MCIntegrator.hpp:161-164)."""
     c = Config()
     c.ndim, c.seed, c.pdf_id, c.move_type, c.srrd, c.veclen, c.ntypes = ndim, seed, pdf_id, move_type, srrd, veclen, ntypes
@@ -92,6 +93,9 @@ def make_config(ndim, seed, pdf_id, obs, nmc, *, move_type=MOVE_ALL, srrd=SRRD_U
         c.obs[i] = Obs(oid, bs, ns, int(fe), et)
     c.nfind, c.ndecorr, c.target_acc, c.nmc = nfind, ndecorr, target_acc, nmc
     c.do_find, c.do_decorr, c.nranks_for_minstat = int(do_find), int(do_decorr), nranks
+    c.srrd_npar = len(srrd_par)
+    for i, v in enumerate(srrd_par):
+        c.srrd_par[i] = v
     return c
 
 

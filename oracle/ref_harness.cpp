@@ -117,6 +117,39 @@ static EstimatorType to_estim(int t)
     }
 }
 
+// A move built around a pre-made distribution, as user code does (include/mci/SRRDAllMove.hpp:45-58, SRRDVecMove.hpp:41-68, test/ut5/main.cpp:110-113)
+template <class AllMoveT, class VecMoveT, class Dist>
+static void set_custom_move(MCI &mci, const orc_config_t &c, int ntypes, const int * tends, const Dist &dist)
+{
+    if (c.move_type == ORC_MOVE_ALL) {
+        AllMoveT mv(c.ndim, ntypes, ntypes > 1 ? tends : nullptr, DEFAULT_MRT2STEP, &dist);
+        mci.setTrialMove(mv);
+    }
+    else {
+        const int veclen = std::max(1, c.veclen);
+        VecMoveT mv(c.ndim/veclen, veclen, ntypes, ntypes > 1 ? tends : nullptr, DEFAULT_MRT2STEP, &dist);
+        mci.setTrialMove(mv);
+    }
+}
+
+static void set_parameterised_move(MCI &mci, const orc_config_t &c, int ntypes, const int * tends)
+{
+    const double p0 = c.srrd_par[0], p1 = (c.srrd_npar > 1) ? c.srrd_par[1] : 1.;
+    if (c.move_type != ORC_MOVE_ALL && c.move_type != ORC_MOVE_VEC) { throw std::invalid_argument("ref_harness: distribution parameters need an all- or vec-move"); }
+    switch (c.srrd) {
+    case 1: set_custom_move<GaussianAllMove, GaussianVecMove>(mci, c, ntypes, tends, std::normal_distribution<double>(0., p0)); break;
+    case 2: set_custom_move<StudentAllMove, StudentVecMove>(mci, c, ntypes, tends, std::student_t_distribution<double>(p0)); break;
+    case 3: set_custom_move<CauchyAllMove, CauchyVecMove>(mci, c, ntypes, tends, std::cauchy_distribution<double>(0., p0)); break;
+    case 4: set_custom_move<ExponentialAllMove, ExponentialVecMove>(mci, c, ntypes, tends, SymmetrizedPRRD<std::exponential_distribution<double>>(std::exponential_distribution<double>(p0))); break;
+    case 5: set_custom_move<GammaAllMove, GammaVecMove>(mci, c, ntypes, tends, SymmetrizedPRRD<std::gamma_distribution<double>>(std::gamma_distribution<double>(p0, p1))); break;
+    case 6: set_custom_move<WeibullAllMove, WeibullVecMove>(mci, c, ntypes, tends, SymmetrizedPRRD<std::weibull_distribution<double>>(std::weibull_distribution<double>(p0, p1))); break;
+    case 7: set_custom_move<LognormalAllMove, LognormalVecMove>(mci, c, ntypes, tends, SymmetrizedPRRD<std::lognormal_distribution<double>>(std::lognormal_distribution<double>(p0, p1))); break;
+    case 8: set_custom_move<ChisqAllMove, ChisqVecMove>(mci, c, ntypes, tends, SymmetrizedPRRD<std::chi_squared_distribution<double>>(std::chi_squared_distribution<double>(p0))); break;
+    case 9: set_custom_move<FisherAllMove, FisherVecMove>(mci, c, ntypes, tends, SymmetrizedPRRD<std::fisher_f_distribution<double>>(std::fisher_f_distribution<double>(p0, p1))); break;
+    default: throw std::invalid_argument("ref_harness: this distribution takes no parameters");
+    }
+}
+
 static void configure(MCI &mci, const orc_config_t &c)
 {
     mci.setSeed(c.seed);
@@ -128,7 +161,8 @@ static void configure(MCI &mci, const orc_config_t &c)
     static const SRRDType kinds[10] = {SRRDType::Uniform, SRRDType::Gaussian, SRRDType::Student, SRRDType::Cauchy, SRRDType::Exponential,
                                        SRRDType::Gamma, SRRDType::Weibull, SRRDType::Lognormal, SRRDType::Chisq, SRRDType::Fisher};
     const SRRDType srrd = kinds[c.srrd];
-    if (c.move_type == ORC_MOVE_ALL) {
+    if (c.srrd_npar > 0) { set_parameterised_move(mci, c, ntypes, tends.data()); }
+    else if (c.move_type == ORC_MOVE_ALL) {
         mci.setTrialMove(srrd, 0, ntypes, ntypes > 1 ? tends.data() : nullptr);
     }
     else if (c.move_type == ORC_MOVE_VEC) {

@@ -124,6 +124,24 @@ RUNS = {
     "srrd_lognormal_all": dict(ndim=3, seed=206, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=8192, srrd=7, steps=(0.3,)),
     "srrd_chisq_vec": dict(ndim=6, seed=207, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 2)], nmc=8192, move_type=orc.MOVE_VEC, veclen=3, srrd=8, steps=(0.4,)),
     "srrd_fisher_all": dict(ndim=1, seed=208, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 32, 1)], nmc=8192, srrd=9, steps=(0.5,), lb=-6., ub=6.),
+    # --- moves built around a pre-made distribution with non-default parameters (include/mci/SRRDAllMove.hpp:45-58; ut5's StudentAllMove(ndim, 0.05,
+    #     &student_t(2)) with its automatic calibration, test/ut5/main.cpp:110-125). srrd_par: Gaussian stddev; Student n; Cauchy b; Exponential lambda;
+    #     Gamma alpha, beta; Weibull a, b; Lognormal m, s; Chisq n; Fisher m, n. The *_vec runs pin a quirk: the reference's vec-move clone drops the
+    #     distribution (include/mci/SRRDVecMove.hpp:30-33), so MCI samples those with the DEFAULT parameters whatever was passed.
+    "ut5_student2_all": dict(ndim=3, seed=5005, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XND, 16, 1)], nmc=8192, srrd=2, srrd_par=(2.0,),
+                             x0=(0.5, -0.5, 0.25), do_find=True, do_decorr=True),
+    "par_gauss_all": dict(ndim=3, seed=301, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=4096, srrd=1, srrd_par=(0.5,), steps=(1.3,)),
+    "par_student5_vec": dict(ndim=4, seed=302, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 8, 1)], nmc=4096, move_type=orc.MOVE_VEC, veclen=2, srrd=2, srrd_par=(5.0,),
+                             steps=(0.6,)),
+    "par_cauchy_all": dict(ndim=2, seed=303, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1)], nmc=4096, srrd=3, srrd_par=(0.25,), steps=(1.0,)),
+    "par_exponential_all": dict(ndim=3, seed=304, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XYZSQUARED, 0, 1)], nmc=4096, srrd=4, srrd_par=(2.5,), steps=(1.5,)),
+    "par_gamma_vec": dict(ndim=3, seed=305, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 16, 1)], nmc=4096, move_type=orc.MOVE_VEC, veclen=1, srrd=5,
+                          srrd_par=(2.5, 0.5), steps=(1.0,)),
+    "par_weibull_all": dict(ndim=2, seed=306, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2SUM, 1, 1)], nmc=4096, srrd=6, srrd_par=(1.5, 0.8), steps=(0.7,)),
+    "par_lognormal_all": dict(ndim=3, seed=307, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1)], nmc=4096, srrd=7, srrd_par=(-0.5, 0.6), steps=(0.5,)),
+    "par_chisq_vec": dict(ndim=6, seed=308, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 2)], nmc=4096, move_type=orc.MOVE_VEC, veclen=3, srrd=8, srrd_par=(3.0,),
+                          steps=(0.2,)),
+    "par_fisher_all": dict(ndim=1, seed=309, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 32, 1)], nmc=4096, srrd=9, srrd_par=(4.0, 6.0), steps=(0.5,), lb=-6., ub=6.),
     # --- edge cases
     "vec_ortho_types": dict(ndim=6, seed=31, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 4, 1), (orc.OBS_X2SUM, 1, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=2,
                             ntypes=3, type_ends=[2, 4, 6], steps=(1.5, 2.5, 3.5), lb=[-2., -3., -2., -3., -2., -3.], ub=[2., 3., 2., 3., 2., 3.],
@@ -156,7 +174,7 @@ DUMP_OBS_FREQ, DUMP_WLK_FREQ = 100, 250
 
 def in_oracle(name):
     """The plain-C oracle restates the uniform and normal proposal distributions; the rest is pinned by the goldens only."""
-    return RUNS[name].get("srrd", 0) < 2 and all(tuple(o)[0] != orc.OBS_DEPENDENT for o in RUNS[name]["obs"])
+    return RUNS[name].get("srrd", 0) < 2 and not RUNS[name].get("srrd_par") and all(tuple(o)[0] != orc.OBS_DEPENDENT for o in RUNS[name]["obs"])
 
 
 # configurations whose step callback sums are pinned by the reference (oracle/ref_harness.cpp: mciref_run_callback)

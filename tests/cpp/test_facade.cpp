@@ -68,6 +68,46 @@ struct CountingCallback {
     }
 };
 
+// A user-defined domain (the reference's DomainInterface is user-subclassable, include/mci/DomainInterface.hpp:26-55): a box with REFLECTING walls
+// [lo, hi]^ndim. Host methods as in the reference; deviceFunctor() names the device twin of applyDomain / scaleToDomain.
+class ReflectingBox final: public DomainInterface
+{
+    const double _lo, _hi;
+
+protected:
+    DomainInterface * _clone() const final { return new ReflectingBox(ndim, _lo, _hi); }
+
+public:
+    ReflectingBox(int n_dim, double lo, double hi): DomainInterface(n_dim), _lo(lo), _hi(hi) {}
+    void applyDomain(double x[]) const final
+    {
+        for (int i = 0; i < ndim; ++i) {
+            while (x[i] < _lo || x[i] > _hi) { x[i] = (x[i] < _lo) ? 2.*_lo - x[i] : 2.*_hi - x[i]; }
+        }
+    }
+    void scaleToDomain(double normX[]) const final
+    {
+        for (int i = 0; i < ndim; ++i) { normX[i] = _lo + normX[i]*(_hi - _lo); }
+    }
+    void getSizes(double dimSizes[]) const final { std::fill(dimSizes, dimSizes + ndim, _hi - _lo); }
+    double getVolume() const final { return pow(_hi - _lo, ndim); }
+    DeviceFunctor deviceFunctor() const final
+    {
+        return DeviceFunctor("ReflectingBox", "user::ReflectingBox", R"(
+namespace user {
+struct ReflectingBox {
+    static constexpr int NPAR = 2;
+    const double * par; // lo, hi
+    __device__ void wrap(int, double & x) const
+    {
+        while (x < par[0] || x > par[1]) { x = (x < par[0]) ? 2.*par[0] - x : 2.*par[1] - x; }
+    }
+    __device__ double scale(int, double u01) const { return par[0] + u01*(par[1] - par[0]); }
+};
+})", {_lo, _hi});
+    }
+};
+
 template <class E, class F>
 static bool throws(F f)
 {
@@ -190,6 +230,62 @@ static void test_gpu()
         mci.integrate(32768, avg, err);
         for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
         assert(fabs(mci.getAcceptanceRate() - 0.85) < 0.06);
+    }
+    { // test/ut5/main.cpp:110-137, i == 0 — customised Student-t all-move built around a pre-made distribution object, and the uniform vec-move with one
+        MCI mci(3);
+        mci.setSeed(1337);
+        mci.setNWalkers(128);
+        auto customStudentDist = std::student_t_distribution<double>(2);
+        auto defaultUniformDist = std::uniform_real_distribution<double>(-1., 1.); // because we can
+        StudentAllMove customAllMove(mci.getNDim(), 0.05, &customStudentDist);
+        UniformVecMove customVecMove(mci.getNDim(), 1, 0.1, &defaultUniformDist);
+        assert(customAllMove.getSRRDParams().size() == 1 && customAllMove.getSRRDParams()[0] == 2. && customVecMove.getSRRDParams().empty());
+        mci.setTrialMove(customAllMove);
+        mci.addSamplingFunction(Gauss(3));
+        mci.addObservable(XSquared(), 1, 1);
+        mci.addObservable(X2(3), 1, 1);
+        mci.integrate(32768, avg, err, true, false);
+        for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
+        assert(fabs(mci.getAcceptanceRate() - 0.5) < 0.05);
+        // symmetrised gamma with half-integer shape; shapes without a fixed-count sampler are refused in the Philox modes, asymmetric objects always
+        auto gam = SymmetrizedPRRD<std::gamma_distribution<double>>(std::gamma_distribution<double>(2.5, 0.5));
+        mci.setTrialMove(GammaAllMove(3, 0.3, &gam));
+        assert(mci.getTrialMove().getSRRDParams().size() == 2);
+        mci.integrate(32768, avg, err, false, false);
+        for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
+        auto gam2 = SymmetrizedPRRD<std::gamma_distribution<double>>(std::gamma_distribution<double>(2.3, 0.5));
+        assert(throws<std::invalid_argument>([&] { mci.setTrialMove(GammaAllMove(3, 0.3, &gam2)); mci.integrate(1024, avg, err, false, false); }));
+        // the reference's vec-move clone drops the distribution (include/mci/SRRDVecMove.hpp:30-33): MCI holds a default-parameter move
+        GammaVecMove gv(3, 1, 0.8, &gam);
+        assert(gv.getSRRDParams().size() == 2);
+        mci.setTrialMove(gv);
+        assert(mci.getTrialMove().getSRRDParams().empty() && mci.getTrialMove().getSRRDType() == SRRDType::Gamma);
+        auto shifted = std::normal_distribution<double>(1., 2.);
+        assert(throws<std::invalid_argument>([&] { GaussianAllMove bad(3, 0.1, &shifted); }));
+        auto wide = std::uniform_real_distribution<double>(-2., 2.);
+        assert(throws<std::invalid_argument>([&] { UniformAllMove bad(3, 0.1, &wide); }));
+    }
+    { // user-defined domain: exp(-r^2) restricted to the reflecting box [-1, 1.5]^3, and plain sampling of the box without a sampling function
+        MCI mci(3);
+        mci.setSeed(4242);
+        mci.setNWalkers(512);
+        mci.setDomain(ReflectingBox(3, -1., 1.5));
+        const double far[3] = {3.2, -2.6, 0.4};
+        mci.setX(far); // reflected into the box by the host twin: 3.2 -> -0.2, -2.6 -> 0.6
+        assert(fabs(mci.getX(0) + 0.2) < 1e-12 && fabs(mci.getX(1) - 0.6) < 1e-12 && mci.getX(2) == 0.4);
+        mci.addSamplingFunction(Gauss(3));
+        mci.addObservable(XND(3), 1, 1);
+        mci.integrate(8192, avg, err, true, true);
+        // <x> of exp(-x^2) on [-1, 1.5]: (e^{-1} - e^{-2.25})/2 / (sqrt(pi)/2 (erf(1) + erf(1.5)))
+        const double want = 0.5*(exp(-1.) - exp(-2.25))/(0.5*sqrt(M_PI)*(erf(1.) + erf(1.5)));
+        for (int i = 0; i < 3; ++i) { assert(err[i] > 0. && fabs(avg[i] - want) < 4.*err[i]); }
+        assert(mci.getMRT2Step(0) <= 0.5*2.5); // calibrated step capped at half the domain size (src/MCIntegrator.cpp:151-155)
+        for (int i = 0; i < 3; ++i) { assert(mci.getX(i) >= -1. && mci.getX(i) <= 1.5); }
+        mci.clearSamplingFunctions();
+        mci.clearObservables();
+        mci.addObservable(XND(3), 1, 1);
+        mci.integrate(8192, avg, err, false, false); // no pdf: uniform over the box, result times the volume
+        for (int i = 0; i < 3; ++i) { assert(fabs(avg[i] - 0.25*pow(2.5, 3)) < 4.*err[i]); }
     }
     { // replay mode, 1 walker: bit-exact reference numbers (generated from the compiled reference)
         MCI mci(3);

@@ -69,10 +69,13 @@ def build_mci(m, spec, nwalkers=1, mode=None, seeds=None, placement=None):
     ntypes = kw.get("ntypes", 1)
     te = kw.get("type_ends")
     srrd = m.SRRDType(kw.get("srrd", 0))
+    par = kw.get("srrd_par") or None
     if mt == orc.MOVE_ALL:
-        mci.setTrialMove(srrd, 0, ntypes, te)
+        mci.setTrialMove(srrd, 0, ntypes, te, params=par)
     elif mt == orc.MOVE_VEC:
-        mci.setTrialMove(srrd, max(1, kw.get("veclen", 1)), ntypes, te)
+        # the reference drops a vec-move's pre-made distribution when MCI clones the move (include/mci/SRRDVecMove.hpp:30-33): the goldens of the
+        # par_*_vec runs are those of the DEFAULT distribution, and the C++ facade mirrors that (include/mci/TrialMoveInterface.hpp: SRRDVecMove::_clone)
+        mci.setTrialMove(srrd, max(1, kw.get("veclen", 1)), ntypes, te, params=None)
     else:
         sub = []
         if kw.get("ms_sub_pdf_id", 0):

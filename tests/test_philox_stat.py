@@ -212,6 +212,68 @@ def test_every_srrd_distribution_samples_the_target(srrd, mcig):
         assert np.all(np.abs(avg - 0.5) < 5*cw), (srrd, veclen, avg, cw)
 
 
+FLAT_PDF_SRC = """struct FlatPDF { static constexpr int NPAR = 0; static constexpr bool HAS_UPDATE = false; static constexpr bool ELEMENTWISE = false; const double * par;
+  template <class X, class P> __device__ void protoFunction(const X &, P & pv) const { pv[0] = 0.; }
+  template <class P> __device__ double samplingFunction(const P &) const { return 1.; }
+  template <class PO, class PN> __device__ double acceptanceFunction(const PO &, const PN &) const { return 1.; } };"""
+
+PARAM_LAWS = [  # (SRRDType, parameters, scipy law of the value (two-sided) or of its magnitude (symmetrised positive laws))
+    (1, (0.5,), "norm", dict(scale=0.5), False), (2, (2.0,), "t", dict(df=2.0), False), (2, (5.5,), "t", dict(df=5.5), False),
+    (3, (0.25,), "cauchy", dict(scale=0.25), False), (4, (2.5,), "expon", dict(scale=1/2.5), True), (5, (2.5, 0.5), "gamma", dict(a=2.5, scale=0.5), True),
+    (5, (3.0, 2.0), "gamma", dict(a=3.0, scale=2.0), True), (6, (1.5, 0.8), "weibull_min", dict(c=1.5, scale=0.8), True),
+    (7, (-0.5, 0.6), "lognorm", dict(s=0.6, scale=np.exp(-0.5)), True), (8, (3.0,), "chi2", dict(df=3.0), True), (9, (4.0, 6.0), "f", dict(dfn=4.0, dfd=6.0), True),
+    # the default-parameter closed forms, through the same check
+    (2, (), "t", dict(df=1.0), False), (4, (), "expon", dict(), True), (7, (), "lognorm", dict(s=1.0), True), (8, (), "chi2", dict(df=1.0), True),
+    (9, (), "f", dict(dfn=1.0, dfd=1.0), True),
+]
+
+
+@pytest.mark.parametrize("srrd,par,law,kw,positive", PARAM_LAWS)
+def test_parameterised_proposals_follow_their_law(srrd, par, law, kw, positive, mcig):
+    """Moves built around a pre-made distribution (mcig_set_srrd_params; reference: the rdist constructor argument, include/mci/SRRDAllMove.hpp:45-58):
+    the Philox-mode closed forms must produce exactly that law. Under a flat sampling function every proposal is accepted, so the increments of the
+    stored positions ARE step x draw: Kolmogorov-Smirnov against scipy's law (two-sided laws directly; symmetrised positive laws by magnitude, plus a
+    fair sign)."""
+    from scipy import stats
+    mcig.register_plugin(0, "FlatPDF", "FlatPDF", FLAT_PDF_SRC, ndim=0, nvalues=1)
+    mci = mcig.MCI(1)
+    mci.setRngMode(0)
+    mci.setSeed(4000 + 10*srrd + len(par))
+    mci.setNWalkers(64)
+    mci.setTrialMove(mcig.SRRDType(srrd), 0, params=par or None)
+    mci.setMRT2Step(1.0)
+    mci.addSamplingFunction(mcig.SamplingFunction("FlatPDF"))
+    mci.addObservable(mcig.XND(1), 1, 1, False, mcig.EstimatorType.Noop)
+    n = 8192
+    mci.integrate(n, False, False)
+    assert mci.getAcceptanceRate() == 1.0
+    d = np.concatenate([np.diff(mci.obsData(0, walker=w, nobs=1)[:, 0]) for w in range(0, 64, 4)])
+    # heavy tails: the walker drifts far from 0 and the increments lose low bits; nothing a distribution test sees
+    if positive:
+        assert abs(np.mean(d > 0) - 0.5) < 5*0.5/np.sqrt(d.size)
+        d = np.abs(d)
+    ks = stats.kstest(d, getattr(stats, law)(**kw).cdf)
+    assert ks.pvalue > 1e-4, (srrd, par, ks)
+
+
+def test_parameterised_proposals_without_fixed_count_sampler_are_refused(mcig):
+    from mcintegratorplusplus_b200._capi import McigError
+    mci = mcig.MCI(2)
+    mci.setRngMode(0)
+    mci.addSamplingFunction(mcig.Gauss(2))
+    mci.addObservable(mcig.XND(2), 0, 1)
+    mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.3, 1.0))
+    with pytest.raises(McigError, match="multiples of 1/2"):
+        mci.prebuild()
+    with pytest.raises(McigError, match="takes 2 parameter"):
+        mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.0,))
+    with pytest.raises(McigError, match="positive"):
+        mci.setTrialMove(mcig.SRRDType.Student, 0, params=(-1.0,))
+    mci.setRngMode(2)  # replay mode consumes the libstdc++ outputs of any parameter set
+    mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.3, 1.0))
+    mci.prebuild()
+
+
 def test_philox_rounds_option(mcig):
     """Philox4x32-7 (opt-in) is a different, still valid stream: same expectation, different per-walker values."""
     from mcintegratorplusplus_b200._capi import McigError

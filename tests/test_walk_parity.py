@@ -51,6 +51,39 @@ def test_replay_vs_oracle_and_golden(name, mcig, oracle, golden_runs):
     assert _close(err, ref["err"], ERR_RTOL, atol=1e-18), (err, ref["err"])
 
 
+USER_PERIODIC_SRC = """template <int NDIM> struct UserPeriodic { static constexpr int NPAR = 2*NDIM; const double * par; // lb[NDIM], ub[NDIM]
+  __device__ void wrap(int i, double & x) const { const double l = par[i], u = par[NDIM + i]; while (x < l) { x += u - l; } while (x > u) { x -= u - l; } }
+  __device__ double scale(int i, double u01) const { return par[i] + u01*(par[NDIM + i] - par[i]); } };"""
+
+
+@pytest.mark.parametrize("placement", [None, 1, 2])
+@pytest.mark.parametrize("name", ["ut2_irange", "vec_ortho_types", "ms_ortho", "nopdf_box", "exbasic_1", "gauss_vec6_v3", "par_fisher_all"])
+def test_user_defined_domain_functor_reproduces_the_builtin_periodic_domain(name, placement, mcig, golden_runs):
+    """MCI::setDomain with a user-defined DomainInterface (device functor of plugin kind MCIG_PLUGIN_DOMAIN): a functor restating the periodic
+    wrap (src/OrthoPeriodicDomain.cpp:38-68) must reproduce the reference's goldens of the setIRange runs bit for bit -- all-, vec- and
+    MultiStep moves, plain sampling of the box without sampling function (scaleToDomain + volume), calibration with the step capped by the
+    domain size -- on every state placement."""
+    spec = configs.RUNS[name]
+    g = golden_runs[name]
+    ndim = spec["ndim"]
+    lb = np.full(ndim, spec["lb"], dtype=float) if np.isscalar(spec["lb"]) else np.asarray(spec["lb"], dtype=float)
+    ub = np.full(ndim, spec["ub"], dtype=float) if np.isscalar(spec["ub"]) else np.asarray(spec["ub"], dtype=float)
+    mcig.register_plugin(3, "UserPeriodic", "UserPeriodic<{ndim}>", USER_PERIODIC_SRC, ndim=0, nvalues=0, npar=0)
+    mci = build_mci(mcig, spec, placement=placement)
+    x0 = mci.getX()
+    with pytest.raises(Exception, match="number of functor parameters"):
+        mci.setDomain(mcig.Domain("UserPeriodic", list(lb)), ub - lb, float(np.prod(ub - lb)))
+    mcig.register_plugin(3, "UserPeriodic%d" % ndim, "UserPeriodic<{ndim}>", USER_PERIODIC_SRC, ndim=ndim, nvalues=0, npar=2*ndim)
+    mci.setDomain(mcig.Domain("UserPeriodic%d" % ndim, list(lb) + list(ub)), ub - lb, float(np.prod(ub - lb)))
+    mci.setX(x0)  # (build_mci's setIRange already wrapped the start position; a user domain takes positions as given)
+    avg, err = mci.integrate(spec["nmc"], spec.get("do_find", False), spec.get("do_decorr", False))
+    assert mci.getAcceptanceRate() == float.fromhex(g["acc_rate"])
+    assert list(mci.getX()) == fromhex(g["x_final"])
+    nt = max(1, spec.get("ntypes", 1))
+    assert [mci.getMRT2Step(i) for i in range(nt)] == fromhex(g["steps_final"])
+    assert _close(avg, fromhex(g["avg"]), AVG_RTOL) and _close(err, fromhex(g["err"]), ERR_RTOL, atol=1e-18)
+
+
 @pytest.mark.parametrize("placement", [0, 1, 2])
 @pytest.mark.parametrize("name", ["c1_simple_short", "vec_exp4", "ms_default4", "ms_sub_ut5", "all_types", "vec3_types"])
 def test_register_and_smem_paths_agree(name, placement, mcig, oracle):
