@@ -375,6 +375,14 @@ public:
     void setAllreduce(mcig_allreduce_fn fn, void * user) { detail::check(mcig_set_allreduce(_ctx, fn, user)); }
     void getCrossWalkerError(double err[]) const { detail::check(mcig_get_cross_walker_error(_ctx, err, mcig_get_result_nobsdim(_ctx))); }
     void setKeepSamples(bool on) { detail::check(mcig_set_keep_samples(_ctx, on ? 1 : 0)); }
+    // engine extras without reference analogue: compile + load every kernel of the configuration now (prebuild), and additionally rehearse the coming
+    // integrate call with every trace undone, so that the first real call runs at steady-state speed (warmup; include/mcig.h)
+    void prebuild() { pushConfiguration(); detail::check(mcig_prebuild(_ctx)); }
+    void warmup(int64_t Nmc, bool doFindMRT2step = true, bool doDecorrelation = true)
+    {
+        pushConfiguration();
+        detail::check(mcig_warmup(_ctx, Nmc, doFindMRT2step ? 1 : 0, doDecorrelation ? 1 : 0));
+    }
     void attachComm(bool on = true) { detail::check(mcig_attach_comm(_ctx, on ? 1 : 0)); }
     void getWalkerResults(double avg[], double err[]) const { detail::check(mcig_get_walker_results(_ctx, avg, err)); }
     mcig_ctx * handle() const { return _ctx; }

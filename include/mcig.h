@@ -254,6 +254,10 @@ int mcig_set_philox_rounds(mcig_ctx * ctx, int rounds);
 int mcig_set_dynamic_scheduling(mcig_ctx * ctx, int mode);
 /* compile (JIT) the kernels the current configuration needs without running them; works without a GPU */
 int mcig_prebuild(mcig_ctx * ctx);
+/* mcig_prebuild plus a rehearsal of the coming integrate(nmc, ., ., do_find, do_decorr) whose every trace is undone (positions, random streams, step
+ * sizes, statistics and results restored, no files written): all device buffers of that call exist at their final size and every kernel has run once,
+ * so the first real call runs at steady-state speed (tests/test_warm_start.py). Sharded jobs: every rank calls it. */
+int mcig_warmup(mcig_ctx * ctx, int64_t nmc, int do_find, int do_decorr);
 /* generated CUDA source of the main walk kernel (for inspection); returns bytes needed */
 int64_t mcig_get_kernel_source(mcig_ctx * ctx, char * buf, int64_t cap);
 /* issue-rate microbenchmarks (roofline denominators): DFMA/s and IMAD/s of the current device */

@@ -88,6 +88,7 @@ SIGNATURES = {
     "mcig_get_staging_chunks": (C.c_int64, [_ctx]),
     "mcig_store_on_file": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int]),
     "mcig_prebuild": (C.c_int, [_ctx]),
+    "mcig_warmup": (C.c_int, [_ctx, C.c_int64, C.c_int, C.c_int]),
     "mcig_get_kernel_source": (C.c_int64, [_ctx, C.c_char_p, C.c_int64]),
     "mcig_measure_peaks": (C.c_int, [C.c_int, _dp, _dp]),
     "mcig_measure_philox_peak": (C.c_int, [C.c_int, _dp]),

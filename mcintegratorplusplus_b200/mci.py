@@ -384,6 +384,10 @@ class MCI:
     def setDynamicScheduling(self, mode): _capi.check(self._lib.mcig_set_dynamic_scheduling(self._ctx, int(mode)))
     def prebuild(self): _capi.check(self._lib.mcig_prebuild(self._ctx))
 
+    def warmup(self, nmc, findMRT2Step=True, initialDecorr=True):
+        """prebuild() plus an undone rehearsal of integrate(nmc, findMRT2Step, initialDecorr): buffers allocated, kernels loaded and run once"""
+        _capi.check(self._lib.mcig_warmup(self._ctx, int(nmc), int(bool(findMRT2Step)), int(bool(initialDecorr))))
+
     def kernelSource(self):
         n = self._lib.mcig_get_kernel_source(self._ctx, None, 0)
         buf = C.create_string_buffer(int(n))
