@@ -159,3 +159,86 @@ def test_all_move_footprint_and_unrolling_rules(mcig, monkeypatch):
     assert "#define MCIG_UNROLL_MAX" not in make(320, placement=2)
     monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_UNROLL_MAX=16")
     assert make(96).count("#define MCIG_UNROLL_MAX") == 1
+
+
+def test_parameterised_move_distributions_host_rules(mcig):
+    """mcig_set_srrd_params (the reference's `rdist` constructor argument, include/mci/SRRDAllMove.hpp:45-58): argument checks mirror the kinds, the
+    Philox-mode kernel receives the parameters as JIT defines (fixed number of uniforms per value), the replay-mode kernel consumes outputs and is
+    the same kernel whatever the parameters; shapes without a fixed-count sampler are refused when the kernel is generated."""
+    from mcintegratorplusplus_b200._capi import McigError
+
+    def make(mode, srrd, par, veclen=0):
+        mci = mcig.MCI(4)
+        mci.setRngMode(mode)
+        mci.addSamplingFunction(mcig.Gauss(4))
+        mci.addObservable(mcig.XND(4), 0, 1)
+        mci.setTrialMove(mcig.SRRDType(srrd), veclen, params=par)
+        mci.prebuild()
+        return mci.kernelSource()
+
+    src = make(0, 2, (2.0,))
+    assert "#define MCIG_SRRD_PARAM 1" in src and "#define MCIG_SRRD_PAR0 0x1p+1" in src and "#define MCIG_SRRD_NU 2" in src
+    assert "#define MCIG_SRRD_NU 5" in make(0, 5, (2.5, 0.5), veclen=2) and "#define MCIG_SRRD_K2A 5" in make(0, 5, (2.5, 0.5))  # 2 exponentials + 2 (half a squared normal) + sign
+    assert "#define MCIG_SRRD_K2A 4" in make(0, 9, (4.0, 6.0)) and "#define MCIG_SRRD_K2B 6" in make(0, 9, (4.0, 6.0))
+    assert "MCIG_SRRD_PARAM" not in make(0, 2, None) and "MCIG_SRRD_PARAM" not in make(2, 2, (2.0,))
+    assert make(2, 5, (2.3, 0.7)) == make(2, 5, None)  # replay: any parameters, same kernel
+    for srrd, par, msg in ((5, (2.3, 0.5), "multiples of 1/2"), (8, (2.5,), "multiples of 1/2"), (9, (3.0, 200.0), "multiples of 1/2")):
+        with pytest.raises(McigError, match=msg):
+            make(0, srrd, par)
+    for srrd, par, msg in ((5, (2.0,), "takes 2 parameter"), (2, (1.0, 2.0), "takes 1 parameter"), (0, (1.0,), "takes 0 parameter"), (3, (0.0,), "positive"),
+                           (7, (0.1, -1.0), "positive")):
+        with pytest.raises(McigError, match=msg):
+            make(0, srrd, par)
+    make(0, 7, (-2.0, 0.5))  # lognormal m: any real
+
+
+def test_user_domain_functor_host_rules(mcig):
+    """mcig_set_domain_plugin: the functor is wrapped behind the kernels' domain interface, its parameters travel in the parameter blob, the host-side
+    rules take the stated sizes / volume (no sampling function: finite volume required); lane-split walkers keep to the built-in domains."""
+    from mcintegratorplusplus_b200._capi import McigError
+    src = """struct HalfLine { static constexpr int NPAR = 1; const double * par;
+      __device__ void wrap(int, double & x) const { if (x < par[0]) { x = 2.*par[0] - x; } }
+      __device__ double scale(int, double u) const { return par[0] + u/(1. - u); } };"""
+    mcig.register_plugin(3, "HalfLine", "HalfLine", src, ndim=0, nvalues=0, npar=1)
+    mci = mcig.MCI(64)
+    mci.setRngMode(0)
+    mci.addSamplingFunction(mcig.ExpNDPDF(64))
+    mci.addObservable(mcig.XND(64), 20, 1)
+    mci.prebuild()
+    assert "walk_kernel_lanes" in mci.kernelSource()
+    mci.setDomain(mcig.Domain("HalfLine", (0.5,)), 2*3.4028234663852886e+38, 0.0)
+    mci.prebuild()
+    s = mci.kernelSource()
+    assert "typedef UserDomain<HalfLine> Domain;" in s and "struct HalfLine" in s and "walk_kernel_lanes" not in s
+    with pytest.raises(McigError, match="wrong number of functor parameters"):
+        mci.setDomain(mcig.Domain("HalfLine", ()), 1.0, 0.0)
+    with pytest.raises(McigError, match="sizes must be positive"):
+        mci.setDomain(mcig.Domain("HalfLine", (0.5,)), 0.0, 0.0)
+    mci.clearSamplingFunctions()
+    with pytest.raises(McigError, match="infinite domain requires a sampling function"):
+        mci.integrate(100, False, False)
+    mci.resetDomain()
+    mci.addSamplingFunction(mcig.ExpNDPDF(64))
+    mci.prebuild()
+    assert "UnboundDomain Domain;" in mci.kernelSource()
+
+
+def test_multistep_cold_position_rules(mcig):
+    """MultiStepMove from 32 coordinates on (element-wise main and sub sampling functions): only the sub-walk's array in shared memory, block size chosen
+    so that the walkers are one full round; below (and with the measurement knob MCIG_MS_COLD_X=0, read once per process) the committed position stays on chip with the 128-thread rule."""
+    def make(ndim, sub=True, w=65536):
+        mci = mcig.MCI(ndim)
+        mci.setRngMode(0)
+        mci.setNWalkers(w)
+        mci.addSamplingFunction(mcig.Gauss(ndim))
+        mci.addObservable(mcig.XND(ndim), 20, 1)
+        mci.setTrialMove(mcig.MoveType.MultiStep, 1, nsteps=ndim, sub_pdfs=[mcig.ExpNDPDF(ndim)] if sub else [])
+        mci.prebuild()
+        return mci.kernelSource()
+
+    s64 = make(64)
+    assert "MS_COLD_X = true" in s64 and "MS_SUB_SUM = true" in s64 and "BLOCK = 224" in s64 and "GmemStore<64>" in s64
+    s32 = make(32)
+    assert "MS_COLD_X = true" in s32 and "RegStore<32>" in s32  # 32 sums stay in registers
+    assert "MS_COLD_X = true" in make(64, sub=False) and "MS_COLD_X = false" in make(16)
+    assert "MS_COLD_X = true" in make(64, w=4096)  # (small jobs: whatever block size fills the machine best; must compile)
