@@ -39,7 +39,7 @@ WALKERS_PER_GPU = 65536
 NMC = 100000
 FP64_INSTR_PER_STEP = 34   # 4 uniform conversions + 6 proposal + 3 proto + 1 exponent + 17 exp + 1 compare + 1 obs + 1 accumulate
 FLOP_PER_STEP = 53
-WALK_DRAM_BYTES_PER_LAUNCH = 1586176  # ncu dram__bytes_read.sum (+ 0 written) of one mcig_walk_dyn launch, profiles/r01_walk_r1f_dyn_ncu_raw.csv
+WALK_DRAM_BYTES_PER_LAUNCH = 1586432  # ncu dram__bytes_read.sum (+ 0 written) of one mcig_walk_dyn launch, profiles/r02z_walk_ncu_raw.csv
 METRIC = "metropolis_samples_per_sec"
 WORKLOAD = "bench_throughput_3G: ThreeDimGaussianPDF ndim=3 + XSquared, uniform all-move step 1.0, SimpleAccumulator, 65536 walkers/GPU x 1e5 steps"
 FP64_LANES_PER_SM, N_SM = 64, 148
@@ -609,14 +609,14 @@ def main():
             "roofline": {"bound": "fp64_issue", "achieved": achieved/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s", "frac": achieved/peaks[0],
                          "peak_nominal": nominal/1e9, "frac_nominal": achieved/nominal,
                          "peak_nominal_source": "64 FP64 lanes/SM/clk x 148 SMs x %.0f MHz (clocks.max.sm); the measured DFMA microbenchmark reaches %.2f of it" % (sm_max_mhz, peaks[0]/nominal),
-                         "traffic": WALK_DRAM_BYTES_PER_LAUNCH, "traffic_note": "dram__bytes_read + dram__bytes_write of one walk launch (ncu --set full, profiles/r01_walk_r1f_dyn_ncu_raw.csv): the 1.5 MB of start positions, nothing written; the bound is FP64/ALU issue, not HBM",
+                         "traffic": WALK_DRAM_BYTES_PER_LAUNCH, "traffic_note": "dram__bytes_read + dram__bytes_write of one walk launch (ncu --set full, profiles/r02z_walk_ncu_raw.csv): the 1.5 MB of start positions, nothing written; the bound is FP64/ALU issue, not HBM",
                          "kernel": "mcig_walk (JIT-specialised Metropolis walk)", "kernel_ms_per_step": walk_ms_max/args.steps,
                          "fp64_instr_per_metropolis_step": FP64_INSTR_PER_STEP, "flop_per_metropolis_step": FLOP_PER_STEP,
                          "achieved_tflops": FLOP_PER_STEP*steps_per_s_kernel/1e12, "peak_tflops": 2*peaks[0]/1e12,
                          "peak_source": "DFMA/s measured live by mcig_measure_peaks on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
                          "imad_peak_ginst": peaks[1]/1e9,
-                         "ncu_pipes": {"source": "profiles/r01_walk_r1h_dyn_ncu_raw.csv (ncu --set full of this kernel; not re-measured inside bench.py)",
-                                       "fp64_pipe_active_pct": 16.7, "fma_heavy_pipe_active_pct": 62.1, "alu_pipe_active_pct": 54.2, "issue_slots_busy_pct": 61.3,
+                         "ncu_pipes": {"source": "profiles/r02z_walk_ncu_raw.csv (ncu --set full of this kernel; not re-measured inside bench.py)",
+                                       "fp64_pipe_active_pct": 15.6, "fma_heavy_pipe_active_pct": 58.0, "alu_pipe_active_pct": 50.7, "issue_slots_busy_pct": 57.3,
                                        "note": "the kernel EXECUTES ~12 FP64 instructions per step (FP32 pre-filter of the accept test, cached observable); the 34 above are the algorithmic count the fraction is quoted on"},
                          "rng_bound": {"philox4x32_10_blocks_per_s": philox_peak, "blocks_per_step": 1, "frac": steps_per_s_kernel/philox_peak,
                                        "note": "issue-rate bound of the counter RNG alone (20 IMAD.WIDE.U32 at a quarter of the FP32 rate per block), measured live; "

@@ -71,8 +71,15 @@ private:
             int mt = MCIG_MOVE_ALL;
             if (m.getMoveType() == MoveType::Vec) { mt = MCIG_MOVE_VEC; }
             if (m.getMoveType() == MoveType::MultiStep) { mt = MCIG_MOVE_MULTISTEP; }
-            detail::check(mcig_set_move(_ctx, mt, toSrrd(m.getSRRDType()), m.getVecLen(), m.getNTypes(), m.getNTypes() > 1 ? m.getTypeEnds() : nullptr));
-            if (!m.getSRRDParams().empty()) { detail::check(mcig_set_srrd_params(_ctx, static_cast<int>(m.getSRRDParams().size()), m.getSRRDParams().data())); }
+            const DeviceFunctor mf = m.deviceFunctor();
+            if (!mf.name.empty()) { // user-defined move: its device functor
+                detail::check(mcig_set_move_plugin(_ctx, mf.resolve(MCIG_PLUGIN_MOVE, _ndim, m.getNUniforms()), mf.params.data(), static_cast<int>(mf.params.size()),
+                                                   m.getNTypes(), m.getNTypes() > 1 ? m.getTypeEnds() : nullptr));
+            }
+            else {
+                detail::check(mcig_set_move(_ctx, mt, toSrrd(m.getSRRDType()), m.getVecLen(), m.getNTypes(), m.getNTypes() > 1 ? m.getTypeEnds() : nullptr));
+            }
+            if (mf.name.empty() && !m.getSRRDParams().empty()) { detail::check(mcig_set_srrd_params(_ctx, static_cast<int>(m.getSRRDParams().size()), m.getSRRDParams().data())); }
             if (mt == MCIG_MOVE_MULTISTEP) {
                 const auto & ms = dynamic_cast<const MultiStepMove &>(m);
                 detail::check(mcig_multistep_config(_ctx, ms.getNSteps()));

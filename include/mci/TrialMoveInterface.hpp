@@ -7,6 +7,7 @@
 #define MCIG_MCI_TRIALMOVEINTERFACE_HPP
 
 #include "mci/Clonable.hpp"
+#include "mci/DeviceFunctor.hpp"
 #include "mci/SamplingFunctionInterface.hpp"
 
 #include <algorithm>
@@ -38,6 +39,11 @@ public:
         static const std::vector<double> none;
         return none;
     }
+    // A user-defined move (the reference's interface is meant to be subclassed: include/mci/TrialMoveInterface.hpp:16-70, trialMove(WalkerState &, ...)):
+    // return the device twin of trialMove here (plugin kind MCIG_PLUGIN_MOVE, contract at mcig_set_move_plugin in include/mcig.h) and the number of
+    // uniforms in [0,1) it consumes per step (0 = one per coordinate); getMoveType() is MoveType::All for such a move (all coordinates may change)
+    virtual DeviceFunctor deviceFunctor() const { return DeviceFunctor(); }
+    virtual int getNUniforms() const { return 0; }
     virtual int getVecLen() const { return 1; }
     virtual int getNTypes() const = 0;
     virtual const int * getTypeEnds() const = 0;

@@ -36,7 +36,8 @@ enum { MCIG_MOVE_ALL = 0, MCIG_MOVE_VEC = 1, MCIG_MOVE_MULTISTEP = 2 };
 /* SRRDType, include/mci/Factories.hpp:119-133 (default parameters of createSymRRD<>, include/mci/TrialMoveInterface.hpp:113-187) */
 enum {
     MCIG_SRRD_UNIFORM = 0, MCIG_SRRD_GAUSSIAN = 1, MCIG_SRRD_STUDENT = 2, MCIG_SRRD_CAUCHY = 3, MCIG_SRRD_EXPONENTIAL = 4,
-    MCIG_SRRD_GAMMA = 5, MCIG_SRRD_WEIBULL = 6, MCIG_SRRD_LOGNORMAL = 7, MCIG_SRRD_CHISQ = 8, MCIG_SRRD_FISHER = 9
+    MCIG_SRRD_GAMMA = 5, MCIG_SRRD_WEIBULL = 6, MCIG_SRRD_LOGNORMAL = 7, MCIG_SRRD_CHISQ = 8, MCIG_SRRD_FISHER = 9,
+    MCIG_SRRD_USER = 10 /* internal: the proposal comes from a user-defined move functor (mcig_set_move_plugin) */
 };
 /* include/mci/Factories.hpp:52-59 */
 enum { MCIG_EST_NOOP = 0, MCIG_EST_UNCORRELATED = 1, MCIG_EST_CORRELATED = 2, MCIG_EST_FCBLOCKER = 3, MCIG_EST_MJBLOCKER = 4 };
@@ -47,7 +48,7 @@ enum {
     MCIG_RNG_REPLAY = 2    /* per-walker std::mt19937_64 + libstdc++ distributions generated on the host and consumed by
                               the kernel in the reference's order: bit-exact reference trajectories (parity mode) */
 };
-enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1, MCIG_PLUGIN_CALLBACK = 2, MCIG_PLUGIN_DOMAIN = 3 };
+enum { MCIG_PLUGIN_PDF = 0, MCIG_PLUGIN_OBS = 1, MCIG_PLUGIN_CALLBACK = 2, MCIG_PLUGIN_DOMAIN = 3, MCIG_PLUGIN_MOVE = 4 };
 /* plugin flags (sampling functions) */
 enum {
     MCIG_PLUGIN_HAS_UPDATE = 1,     /* functor overrides updatedAcceptance (selective update for single-vector moves) */
@@ -129,6 +130,17 @@ int mcig_set_move(mcig_ctx * ctx, int move_type, int srrd, int veclen, int ntype
  * Replay mode consumes the libstdc++ outputs of exactly that distribution; the Philox modes sample the same law from a fixed number of uniforms
  * per value, which for Gamma / Chisq / Fisher needs shapes that are multiples of 1/2 (refused with MCIG_ERR_INVALID_ARGUMENT otherwise). */
 int mcig_set_srrd_params(mcig_ctx * ctx, int npar, const double * par);
+/* MCI::setTrialMove(const TrialMoveInterface &) with a user-defined move (the reference's TrialMoveInterface is user-subclassable,
+ * include/mci/TrialMoveInterface.hpp:16-70): a device functor of plugin kind MCIG_PLUGIN_MOVE, registered with nvalues = the number of uniforms in
+ * [0,1) it consumes per step (0 = one per coordinate),
+ *     struct MyMove { static constexpr int NPAR = ...; const double * par;
+ *         template <class XO, class XN, class T, class U>
+ *         __device__ double trialMove(const XO & xold, XN & xnew, const double * steps, T typeOf, const U & u) const; };
+ * fills xnew[0 .. ndim) from xold, the typed step sizes steps[typeOf.of(i)] and u(0) .. u(nvalues - 1), and returns the move's acceptance factor
+ * (1 for symmetric proposals). The engine then applies the domain, evaluates the sampling functions on the whole proposal and accepts when the
+ * accept uniform <= pdf acceptance * that factor (src/MCIntegrator.cpp:329-343). Typed step sizes as in mcig_set_move (calibrated by findMRT2Step).
+ * Replay mode feeds the outputs of std::uniform_real_distribution<double>(0,1) on the walker's std::mt19937_64, in order. */
+int mcig_set_move_plugin(mcig_ctx * ctx, int plugin_id, const double * par, int npar, int ntypes, const int * type_ends);
 int mcig_multistep_config(mcig_ctx * ctx, int nsteps);
 int mcig_multistep_add_pdf(mcig_ctx * ctx, int plugin_id, const double * par, int npar);
 /* MCI::setMRT2Step / getMRT2Step  src/MCIntegrator.cpp:557-585 */

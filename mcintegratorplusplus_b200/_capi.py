@@ -40,6 +40,7 @@ SIGNATURES = {
     "mcig_set_domain_plugin": (C.c_int, [_ctx, C.c_int, _dp, C.c_int, _dp, C.c_double]),
     "mcig_set_move": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "mcig_set_srrd_params": (C.c_int, [_ctx, C.c_int, _dp]),
+    "mcig_set_move_plugin": (C.c_int, [_ctx, C.c_int, _dp, C.c_int, C.c_int, _ip]),
     "mcig_multistep_config": (C.c_int, [_ctx, C.c_int]),
     "mcig_multistep_add_pdf": (C.c_int, [_ctx, C.c_int, _dp, C.c_int]),
     "mcig_get_nsteps_sizes": (C.c_int, [_ctx]),

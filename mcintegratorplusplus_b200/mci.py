@@ -87,6 +87,11 @@ class StepCallback(Plugin):
     kind = 2
 
 
+class Move(Plugin):
+    """A user-defined trial move as a device functor (see include/mcig.h: mcig_set_move_plugin)."""
+    kind = 4
+
+
 class Domain(Plugin):
     """A user-defined (separable) domain as a device functor (see include/mcig.h: mcig_set_domain_plugin)."""
     kind = 3
@@ -242,6 +247,10 @@ class MCI:
         if typeEnds is not None:
             te_arr = np.ascontiguousarray(typeEnds, dtype=np.int32)
             te = te_arr.ctypes.data_as(C.POINTER(C.c_int))
+        if isinstance(move, Move):  # setTrialMove(const TrialMoveInterface &) with a user-defined move functor
+            a, p = _darr(move.par)
+            _capi.check(self._lib.mcig_set_move_plugin(self._ctx, move.plugin_id(), p, len(move.par), ntypes, te))
+            return
         srrd = 0
         if isinstance(move, MoveType):
             mt = int(move)

@@ -49,7 +49,9 @@ enum {
 };
 
 /* trial moves: include/mci/Factories.hpp:108-145 */
-enum { ORC_MOVE_ALL = 0, ORC_MOVE_VEC = 1, ORC_MOVE_MULTISTEP = 2 };
+enum { ORC_MOVE_ALL = 0, ORC_MOVE_VEC = 1, ORC_MOVE_MULTISTEP = 2,
+       ORC_MOVE_USER_DRIFT = 3 /* reference harness only: a user-defined TrialMoveInterface subclass (oracle/ref_harness.cpp: HarnessDriftMove), goldens for
+                                  the device-side move functor; srrd_par[0] = drift */ };
 /* SRRD distribution of the move, include/mci/Factories.hpp:119-133. The C restatement covers 0 and 1; 2..9 (Student, Cauchy,
    Exponential, Gamma, Weibull, Lognormal, Chisq, Fisher) are available through the reference harness only (goldens). */
 enum { ORC_SRRD_UNIFORM = 0, ORC_SRRD_GAUSSIAN = 1 };

@@ -15,6 +15,7 @@ PDF_NONE, PDF_GAUSS3D, PDF_GAUSS, PDF_EXP1D, PDF_EXPND, PDF_NORMLINE = range(6)
 (OBS_XSQUARED, OBS_GAUSSXSQUARED, OBS_XYZSQUARED, OBS_X1D, OBS_XND, OBS_UPDXND, OBS_CONSTVAL, OBS_POLYNOM,
  OBS_X2SUM, OBS_X2, OBS_PARABOLA, OBS_NORMPARABOLA, OBS_DEPENDENT) = range(1, 14)
 MOVE_ALL, MOVE_VEC, MOVE_MULTISTEP = range(3)
+MOVE_USER_DRIFT = 3  # reference harness only: a user-defined TrialMoveInterface subclass (oracle/ref_harness.cpp: HarnessDriftMove), srrd_par = (drift,)
 SRRD_UNIFORM, SRRD_GAUSSIAN = range(2)
 EST_NOOP, EST_UNCORRELATED, EST_CORRELATED, EST_FCBLOCKER, EST_MJBLOCKER = range(5)
 EST_BLOCK = 100

@@ -117,6 +117,45 @@ static EstimatorType to_estim(int t)
     }
 }
 
+// A user-defined trial move (include/mci/TrialMoveInterface.hpp:16-70 is meant to be subclassed) for the golden vectors of the device-side move functor:
+// every coordinate moves by step*(2u - 1) + drift with u ~ U[0,1) drawn from MCI's generator. The proposal density is uniform on an interval that is NOT
+// centred on the old position, so the move's acceptance factor q(x|x')/q(x'|x) is 1 where the reverse move is possible (|step v + 2 drift| <= step, per
+// coordinate) and 0 where it is not: exercises pdfAcc*moveAcc (src/MCIntegrator.cpp:343) without any transcendental in the positions.
+class HarnessDriftMove final: public TypedMoveInterface
+{
+    const double _drift;
+    std::uniform_real_distribution<double> _rd;
+
+protected:
+    TrialMoveInterface * _clone() const final
+    {
+        auto * m = new HarnessDriftMove(_ndim, _ntypes, _typeEnds, 0., _drift);
+        std::copy(_stepSizes, _stepSizes + _ntypes, m->_stepSizes);
+        return m;
+    }
+
+public:
+    HarnessDriftMove(int ndim, int ntypes, const int typeEnds[], double initStepSize, double drift):
+            TypedMoveInterface(ndim, 0, ntypes, typeEnds, initStepSize), _drift(drift), _rd(0., 1.) {}
+    double getChangeRate() const final { return 1.; }
+    void protoFunction(const double[], double[]) final {}
+    double trialMove(WalkerState &wlk, const double[], double[]) final
+    {
+        double macc = 1.;
+        int xidx = 0;
+        for (int tidx = 0; tidx < _ntypes; ++tidx) {
+            while (xidx < _typeEnds[tidx]) {
+                const double d = _stepSizes[tidx]*(2.*_rd(*_rgen) - 1.) + _drift;
+                wlk.xnew[xidx] += d;
+                if (fabs(d + _drift) > _stepSizes[tidx]) { macc = 0.; } // the reverse move -d - ... lies outside the proposal interval
+                ++xidx;
+            }
+        }
+        wlk.nchanged = _ndim;
+        return macc;
+    }
+};
+
 // A move built around a pre-made distribution, as user code does (include/mci/SRRDAllMove.hpp:45-58, SRRDVecMove.hpp:41-68, test/ut5/main.cpp:110-113)
 template <class AllMoveT, class VecMoveT, class Dist>
 static void set_custom_move(MCI &mci, const orc_config_t &c, int ntypes, const int * tends, const Dist &dist)
@@ -161,7 +200,11 @@ static void configure(MCI &mci, const orc_config_t &c)
     static const SRRDType kinds[10] = {SRRDType::Uniform, SRRDType::Gaussian, SRRDType::Student, SRRDType::Cauchy, SRRDType::Exponential,
                                        SRRDType::Gamma, SRRDType::Weibull, SRRDType::Lognormal, SRRDType::Chisq, SRRDType::Fisher};
     const SRRDType srrd = kinds[c.srrd];
-    if (c.srrd_npar > 0) { set_parameterised_move(mci, c, ntypes, tends.data()); }
+    if (c.move_type == ORC_MOVE_USER_DRIFT) {
+        HarnessDriftMove mv(c.ndim, ntypes, ntypes > 1 ? tends.data() : nullptr, DEFAULT_MRT2STEP, c.srrd_par[0]);
+        mci.setTrialMove(mv);
+    }
+    else if (c.srrd_npar > 0) { set_parameterised_move(mci, c, ntypes, tends.data()); }
     else if (c.move_type == ORC_MOVE_ALL) {
         mci.setTrialMove(srrd, 0, ntypes, ntypes > 1 ? tends.data() : nullptr);
     }

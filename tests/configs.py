@@ -142,6 +142,14 @@ RUNS = {
     "par_chisq_vec": dict(ndim=6, seed=308, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 2)], nmc=4096, move_type=orc.MOVE_VEC, veclen=3, srrd=8, srrd_par=(3.0,),
                           steps=(0.2,)),
     "par_fisher_all": dict(ndim=1, seed=309, pdf_id=orc.PDF_EXP1D, obs=[(orc.OBS_X1D, 32, 1)], nmc=4096, srrd=9, srrd_par=(4.0, 6.0), steps=(0.5,), lb=-6., ub=6.),
+    # --- a user-defined trial move (TrialMoveInterface subclass in the reference harness, device functor here): drifted uniform proposal whose
+    #     acceptance factor is 0 or 1 (oracle/ref_harness.cpp: HarnessDriftMove; tests/prod.py: DRIFT_MOVE_SRC); srrd_par = (drift,)
+    "user_drift_all": dict(ndim=3, seed=7101, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 1, 1), (orc.OBS_XYZSQUARED, 8, 1)], nmc=8192,
+                           move_type=orc.MOVE_USER_DRIFT, srrd_par=(0.15,), steps=(0.9,), x0=(0.3, -0.2, 0.1)),
+    "user_drift_types_ortho": dict(ndim=4, seed=7102, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_X2, 1, 1)], nmc=4096, move_type=orc.MOVE_USER_DRIFT, srrd_par=(-0.05,),
+                                   ntypes=2, type_ends=[1, 4], steps=(1.1, 0.7), lb=-2.5, ub=2.5, x0=(1., -1., 0.5, 0.), do_decorr=True),
+    "user_drift_all24": dict(ndim=24, seed=7103, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 16, 1)], nmc=2048, move_type=orc.MOVE_USER_DRIFT, srrd_par=(0.01,),
+                             steps=(0.2,), x0=_alt(24)),
     # --- edge cases
     "vec_ortho_types": dict(ndim=6, seed=31, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_XND, 4, 1), (orc.OBS_X2SUM, 1, 1)], nmc=8192, move_type=orc.MOVE_VEC, veclen=2,
                             ntypes=3, type_ends=[2, 4, 6], steps=(1.5, 2.5, 3.5), lb=[-2., -3., -2., -3., -2., -3.], ub=[2., 3., 2., 3., 2., 3.],
@@ -174,7 +182,7 @@ DUMP_OBS_FREQ, DUMP_WLK_FREQ = 100, 250
 
 def in_oracle(name):
     """The plain-C oracle restates the uniform and normal proposal distributions; the rest is pinned by the goldens only."""
-    return RUNS[name].get("srrd", 0) < 2 and not RUNS[name].get("srrd_par") and all(tuple(o)[0] != orc.OBS_DEPENDENT for o in RUNS[name]["obs"])
+    return RUNS[name].get("srrd", 0) < 2 and not RUNS[name].get("srrd_par") and RUNS[name].get("move_type", 0) != orc.MOVE_USER_DRIFT and all(tuple(o)[0] != orc.OBS_DEPENDENT for o in RUNS[name]["obs"])
 
 
 # configurations whose step callback sums are pinned by the reference (oracle/ref_harness.cpp: mciref_run_callback)

@@ -108,6 +108,43 @@ struct ReflectingBox {
     }
 };
 
+// A user-defined trial move (reference: a TrialMoveInterface subclass with a host trialMove(WalkerState &, ...)): drifted uniform proposal with typed step
+// sizes, acceptance factor 1 where the reverse move lies inside the proposal interval and 0 where it does not.
+class DriftMove final: public TypedMoveInterface
+{
+    const double _drift;
+
+protected:
+    TrialMoveInterface * _clone() const final { return new DriftMove(*this); }
+
+public:
+    DriftMove(int ndim, double initStepSize, double drift): TypedMoveInterface(ndim, 1, nullptr, initStepSize, SRRDType::Uniform), _drift(drift) {}
+    MoveType getMoveType() const final { return MoveType::All; }
+    double getChangeRate() const final { return 1.; }
+    DeviceFunctor deviceFunctor() const final
+    {
+        return DeviceFunctor("DriftMove", "user::DriftMove<{ndim}>", R"(
+namespace user {
+template <int NDIM> struct DriftMove {
+    static constexpr int NPAR = 1;
+    const double * par;
+    template <class XO, class XN, class T, class U>
+    __device__ double trialMove(const XO & xold, XN & xnew, const double * steps, T typeOf, const U & u) const
+    {
+        double macc = 1.;
+        for (int i = 0; i < NDIM; ++i) {
+            const double s = steps[typeOf.of(i)];
+            const double d = s*(2.*u(i) - 1.) + par[0];
+            xnew[i] = xold[i] + d;
+            if (fabs(d + par[0]) > s) { macc = 0.; }
+        }
+        return macc;
+    }
+};
+})", {_drift});
+    }
+};
+
 template <class E, class F>
 static bool throws(F f)
 {
@@ -264,6 +301,21 @@ static void test_gpu()
         assert(throws<std::invalid_argument>([&] { GaussianAllMove bad(3, 0.1, &shifted); }));
         auto wide = std::uniform_real_distribution<double>(-2., 2.);
         assert(throws<std::invalid_argument>([&] { UniformAllMove bad(3, 0.1, &wide); }));
+    }
+    { // user-defined trial move: detailed balance through its own acceptance factor, step calibrated like any typed move
+        MCI mci(3);
+        mci.setSeed(777);
+        mci.setNWalkers(256);
+        mci.setTrialMove(DriftMove(3, 0.3, 0.03));
+        assert(mci.getTrialMove().getNStepSizes() == 1 && mci.getMRT2Step(0) == 0.3);
+        mci.setTargetAcceptanceRate(0.4);
+        mci.addSamplingFunction(Gauss(3));
+        mci.addObservable(XSquared(), 1, 1);
+        mci.addObservable(XND(3), 1, 1);
+        mci.integrate(16384, avg, err, true, true);
+        assert(fabs(avg[0] - 0.5) < 3.5*err[0]);
+        for (int i = 1; i < 4; ++i) { assert(fabs(avg[i]) < 3.5*err[i]); } // <x_i> = 0: a drifted proposal WITHOUT its acceptance factor would bias this
+        assert(fabs(mci.getAcceptanceRate() - 0.4) < 0.06 && mci.getMRT2Step(0) > 0.3);
     }
     { // user-defined domain: exp(-r^2) restricted to the reflecting box [-1, 1.5]^3, and plain sampling of the box without a sampling function
         MCI mci(3);

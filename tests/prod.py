@@ -46,7 +46,26 @@ struct FoldCallback { // the four sums of mciref_run_callback, one set per walke
 """
 
 
+DRIFT_MOVE_SRC = """namespace test_plugins {
+// device twin of oracle/ref_harness.cpp: HarnessDriftMove (a user-defined TrialMoveInterface subclass): x' = x + step (2u - 1) + drift per coordinate,
+// acceptance factor 1 where the reverse move lies inside the proposal interval, else 0
+template <int NDIM> struct DriftMove { static constexpr int NPAR = 1; const double * par;
+  template <class XO, class XN, class T, class U>
+  __device__ double trialMove(const XO & xold, XN & xnew, const double * steps, T typeOf, const U & u) const {
+    double macc = 1.;
+    for (int i = 0; i < NDIM; ++i) {
+      const double s = steps[typeOf.of(i)];
+      const double d = s*(2.*u(i) - 1.) + par[0];
+      xnew[i] = xold[i] + d;
+      if (fabs(d + par[0]) > s) { macc = 0.; }
+    }
+    return macc;
+  } };
+}"""
+
+
 def register_test_plugins(m):
+    m.register_plugin(4, "DriftMove", "test_plugins::DriftMove<{ndim}>", DRIFT_MOVE_SRC, ndim=0, nvalues=0, npar=1)
     m.register_plugin(1, "HarnessDepObs", "test_plugins::HarnessDepObs<{ndim}>", DEP_OBS_SRC, ndim=0, nvalues=2, npar=0, dependent=True)
     m.register_plugin(2, "FoldCallback", "test_plugins::FoldCallback<{ndim}>", CALLBACK_SRC, ndim=0, npar=0)
 
@@ -70,7 +89,9 @@ def build_mci(m, spec, nwalkers=1, mode=None, seeds=None, placement=None):
     te = kw.get("type_ends")
     srrd = m.SRRDType(kw.get("srrd", 0))
     par = kw.get("srrd_par") or None
-    if mt == orc.MOVE_ALL:
+    if mt == orc.MOVE_USER_DRIFT:
+        mci.setTrialMove(m.Move("DriftMove", kw["srrd_par"]), 0, ntypes, te)
+    elif mt == orc.MOVE_ALL:
         mci.setTrialMove(srrd, 0, ntypes, te, params=par)
     elif mt == orc.MOVE_VEC:
         # the reference drops a vec-move's pre-made distribution when MCI clones the move (include/mci/SRRDVecMove.hpp:30-33): the goldens of the

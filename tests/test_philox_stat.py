@@ -274,6 +274,42 @@ def test_parameterised_proposals_without_fixed_count_sampler_are_refused(mcig):
     mci.prebuild()
 
 
+@pytest.mark.parametrize("ndim,placement", [(3, None), (3, 1), (24, None), (80, None)])
+def test_user_defined_move_keeps_detailed_balance(ndim, placement, mcig):
+    """A user-defined trial move (device functor of kind MCIG_PLUGIN_MOVE; the reference's TrialMoveInterface subclasses): a DRIFTED uniform proposal is
+    only correct together with its acceptance factor (0 where the reverse move is impossible). <x_i> = 0 and <x_i^2> = 1/2 under exp(-r^2) on the
+    register, shared-memory and block-by-block draw paths; the same move with the factor forced to 1 is visibly biased."""
+    from prod import register_test_plugins
+    register_test_plugins(mcig)
+    biased = """template <int NDIM> struct DriftNoFactor { static constexpr int NPAR = 1; const double * par;
+      template <class XO, class XN, class T, class U> __device__ double trialMove(const XO & xo, XN & xn, const double * st, T ty, const U & u) const {
+        for (int i = 0; i < NDIM; ++i) { xn[i] = xo[i] + st[ty.of(i)]*(2.*u(i) - 1.) + par[0]; } return 1.; } };"""
+    mcig.register_plugin(4, "DriftNoFactor", "DriftNoFactor<{ndim}>", biased, ndim=0, nvalues=0, npar=1)
+    out = {}
+    for name in ("DriftMove", "DriftNoFactor"):
+        mci = mcig.MCI(ndim)
+        mci.setRngMode(0)
+        mci.setSeed(99)
+        mci.setNWalkers(4096)
+        step = 1.6/ndim**0.5
+        mci.setTrialMove(mcig.Move(name, (0.6*step/ndim,)))  # (the reverse move is impossible with probability drift/step per coordinate)
+        mci.setMRT2Step(step)
+        if placement is not None:
+            mci.setStatePlacement(placement)
+        mci.addSamplingFunction(mcig.Gauss(ndim))
+        mci.addObservable(mcig.XND(ndim), 0, 1)
+        mci.addObservable(mcig.X2(ndim), 0, 1)
+        mci.integrate(2000, False, False)
+        avg, _ = mci.integrate(4000, False, False)
+        out[name] = (avg, mci.crossWalkerError(), mci.getAcceptanceRate())
+    avg, cw, acc = out["DriftMove"]
+    assert 0.05 < acc < 0.9
+    assert np.all(np.abs(avg[:ndim]) < 5*cw[:ndim]) and np.all(np.abs(avg[ndim:] - 0.5) < 5*cw[ndim:]), (avg, cw)
+    bavg, bcw, _ = out["DriftNoFactor"]
+    if ndim == 3:
+        assert np.mean(bavg[:ndim]) > 10*np.mean(bcw[:ndim])  # the drift shows when the factor is dropped
+
+
 def test_philox_rounds_option(mcig):
     """Philox4x32-7 (opt-in) is a different, still valid stream: same expectation, different per-walker values."""
     from mcintegratorplusplus_b200._capi import McigError
