@@ -3,7 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import mcintegratorplusplus_b200 as m
-for nd in (16, 32, 64):
+for nd in ([int(a) for a in sys.argv[1:]] or [16, 32, 64]):
     mci = bench.c3_mci(m, "multistep", nd, 65536, None)
     nmc = max(200, 8000//(2*nd)//20*20)
     mci.integrate(40, False, False)
