@@ -239,7 +239,7 @@ int mcig_estimate_blocks(int64_t n, int ndim, const double * x, int64_t nblocks,
 int mcig_set_block_size(mcig_ctx * ctx, int threads_per_block); /* 0 = automatic */
 int mcig_set_state_placement(mcig_ctx * ctx, int placement);    /* -1 auto, 0 registers, 1 shared memory, 2 global memory (auto picks 2 when a warp of walkers exceeds 227 KiB),
                                                                   * 3 registers of several lanes per walker (uniform all-moves with a SUM_ACCEPTANCE sampling function and
-                                                                  * element-wise observables; auto picks it from 64 coordinates on) */
+                                                                  * element-wise observables; auto picks it from 16 coordinates on) */
 /* Element-wise observables (plugin flag MCIG_PLUGIN_ELEMENTWISE, e.g. XND, X2) in Simple / Block accumulators under single-vector
  * moves: add value x dwell time when a coordinate changes instead of every component at every step. 1 (default): in the Philox
  * modes, replay mode keeps the reference's summation order; 2: in every mode; 0: never. Sums differ by rounding only. */

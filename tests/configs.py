@@ -105,6 +105,8 @@ RUNS = {
     #     Block accumulators of element-wise observables, automatic calibration + decorrelation
     "lanes_all128_auto": dict(ndim=128, seed=12801, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1), (orc.OBS_X2, 1, 2), (orc.OBS_UPDXND, 8, 1)], nmc=4096,
                               ntypes=2, type_ends=[64, 128], steps=(0.2, 0.1), lb=-3., ub=3., x0=_alt(128), nfind=-20, ndecorr=-2000, do_find=True, do_decorr=True),
+    "lanes_all8_b4": dict(ndim=8, seed=801, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 4, 1), (orc.OBS_X2, 1, 1, False, orc.EST_UNCORRELATED)], nmc=2048, steps=(0.6,),
+                          x0=_alt(8)),  # observables of <= 8 components with the uncorrelated estimator: the ones the walk would fuse; lane slices store their series
     "lanes_all192": dict(ndim=192, seed=19201, pdf_id=orc.PDF_EXPND, obs=[(orc.OBS_X2, 16, 1, True, orc.EST_CORRELATED)], nmc=2048, steps=(0.15,), x0=_alt(192)),
     # --- Gaussian proposals (SRRDType::Gaussian: std::normal_distribution, polar method with a cached value)
     "gauss_all": dict(ndim=3, seed=99, pdf_id=orc.PDF_GAUSS3D, obs=[(orc.OBS_XSQUARED, 16, 1)], nmc=16384, srrd=orc.SRRD_GAUSSIAN, steps=(0.6,)),
@@ -191,7 +193,7 @@ C3_SHAPES = ["ms_sub32_b20", "ms_sub64_b20", "ms_nosub32_b20", "ms_nosub64_b20",
              "ndim_vec32_b20", "ndim_vec64_b20"]
 
 # configurations eligible for lane-split walkers, with the lane count placement 3 gives them
-LANE_SPLIT = {"ndim_all16": 2, "ndim_all32_b20": 2, "ndim_all64_b20": 4, "lanes_all128_auto": 8, "lanes_all192": 8}
+LANE_SPLIT = {"lanes_all8_b4": 2, "ndim_all16": 2, "ndim_all32_b20": 2, "ndim_all64_b20": 4, "lanes_all128_auto": 8, "lanes_all192": 8}
 
 CALLBACK_RUNS = ["c1_simple_short", "vec_exp4", "ms_sub16", "auto_default", "ut2_irange", "nopdf_box", "gauss_vec6_v3"]
 

@@ -149,12 +149,13 @@ def test_all_move_footprint_and_unrolling_rules(mcig, monkeypatch):
     monkeypatch.delenv("MCIG_ALL_VPO")
     assert "MS_MAIN_VPO = false" in make(8, placement=None)  # register-resident walkers keep their proto values in registers
     # automatic placement: eligible all-moves (uniform proposal, SUM_ACCEPTANCE sampling function, element-wise observables) spread one
-    # walker over several lanes from 64 coordinates on; below, and for ineligible configurations, the rules above apply
+    # walker over several lanes from 16 coordinates on; below, and for ineligible configurations, the rules above apply
     auto64 = make(64, placement=None)
     assert "walk_kernel_lanes" in auto64 and "LANES = 4, NL = 16" in auto64
     assert "LANES = 8, NL = 16" in make(128, placement=None) and "LANES = 16, NL = 16" in make(256, placement=None)
-    assert "walk_kernel_smem" in make(32, placement=None)
-    assert "LANES = 2, NL = 16" in make(32, placement=3)
+    assert "LANES = 2, NL = 16" in make(32, placement=None) and "LANES = 2, NL = 24" in make(48, placement=None) and "LANES = 2, NL = 8" in make(16, placement=None)
+    assert "walk_kernel_reg" in make(8, placement=None) and "walk_kernel_smem" in make(20, placement=None)  # (20 does not split into lanes of 4 k coordinates)
+    assert "LANES = 2, NL = 4" in make(8, placement=3)
     assert "#define MCIG_UNROLL_MAX 256" in make(96)
     assert "#define MCIG_UNROLL_MAX" not in make(320, placement=2)
     monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_UNROLL_MAX=16")
