@@ -57,6 +57,8 @@ for it in range(n):
                 col += w
             if ref is None:
                 ref = avg.copy()
+            else:  # same Philox streams whatever the placement: the numbers agree up to summation order
+                assert np.allclose(avg, ref, rtol=1e-9, atol=1e-11), ("placements disagree", float(np.max(np.abs(avg - ref))))
         except McigError as ex:
             msg = str(ex)
             if "cuda" in msg.lower() or "CUDA" in msg:
