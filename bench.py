@@ -229,10 +229,15 @@ def run_reference_arm(args, rank, world):
         walls.append(wall)
     pool.close()
     total = sum(walls)
-    value = args.steps*pool.nproc*REF_NMC/total
-    sample = "%d independent chains (one per host core) x %.1e Metropolis steps of the same integrand per bench step; %s" % (pool.nproc, REF_NMC, pool.flags)
+    # The box's host cores are shared with other jobs (the same arm read 2.3e8 .. 3.3e8 samples/s on boxes of this pool within an hour): the value is the
+    # FASTEST of the K steps, i.e. the reference at its least disturbed -- the conservative denominator for any GPU/CPU ratio; the mean over all K steps
+    # is reported next to it
+    best = min(walls)
+    value = pool.nproc*REF_NMC/best
+    sample = ("%d independent chains (one per host core) x %.1e Metropolis steps of the same integrand per bench step, fastest of %d steps (mean over all: %.4g samples/s); %s"
+              % (pool.nproc, REF_NMC, args.steps, args.steps*pool.nproc*REF_NMC/total, pool.flags))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3*total/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3*best, "mean_value": args.steps*pool.nproc*REF_NMC/total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": bench_config(world),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": pool.nproc, "kind": pool.kind, "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -628,7 +633,7 @@ def main():
             "result": {"avg": float(avg[0]), "err": float(err[0]), "acceptance": float(rate), "cross_walker_err_local": cw_local},
         }
         if pool is not None and world == 1:
-            v, wall, outs = pool.run(c2_kw(), REF_NMC)
+            v, wall, outs = max((pool.run(c2_kw(), REF_NMC) for _ in range(2)), key=lambda r: r[0])  # the less disturbed of two samples (shared host cores)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": pool.nproc, "kind": pool.kind,
                                     "sample": "%d independent chains (one per host core) x %.1e Metropolis steps of the same integrand, %.1f s wall; %s" % (pool.nproc, REF_NMC, wall, pool.flags)}
         if secondary is not None:
