@@ -128,7 +128,8 @@ int mcig_set_move(mcig_ctx * ctx, int move_type, int srrd, int veclen, int ntype
  * (which resets to the defaults). par: Gaussian {stddev}; Student {n}; Cauchy {b}; Exponential {lambda}; Gamma {alpha, beta}; Weibull {a, b};
  * Lognormal {m, s}; Chisq {n}; Fisher {m, n}; npar = 0 restores the defaults. Locations stay 0 (a move distribution must be symmetric).
  * Replay mode consumes the libstdc++ outputs of exactly that distribution; the Philox modes sample the same law from a fixed number of uniforms
- * per value, which for Gamma / Chisq / Fisher needs shapes that are multiples of 1/2 (refused with MCIG_ERR_INVALID_ARGUMENT otherwise). */
+ * per value: closed forms, for Gamma / Chisq / Fisher shapes that are multiples of 1/2 sums of exponentials, for any other shape Marsaglia & Tsang's
+ * test with 6 tries per value (all of them fail with probability < 2e-8; the proposal stays symmetric, so the chain stays exact). */
 int mcig_set_srrd_params(mcig_ctx * ctx, int npar, const double * par);
 /* MCI::setTrialMove(const TrialMoveInterface &) with a user-defined move (the reference's TrialMoveInterface is user-subclassable,
  * include/mci/TrialMoveInterface.hpp:16-70): a device functor of plugin kind MCIG_PLUGIN_MOVE, registered with nvalues = the number of uniforms in

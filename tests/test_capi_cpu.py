@@ -183,9 +183,13 @@ def test_parameterised_move_distributions_host_rules(mcig):
     assert "#define MCIG_SRRD_K2A 4" in make(0, 9, (4.0, 6.0)) and "#define MCIG_SRRD_K2B 6" in make(0, 9, (4.0, 6.0))
     assert "MCIG_SRRD_PARAM" not in make(0, 2, None) and "MCIG_SRRD_PARAM" not in make(2, 2, (2.0,))
     assert make(2, 5, (2.3, 0.7)) == make(2, 5, None)  # replay: any parameters, same kernel
-    for srrd, par, msg in ((5, (2.3, 0.5), "multiples of 1/2"), (8, (2.5,), "multiples of 1/2"), (9, (3.0, 200.0), "multiples of 1/2")):
-        with pytest.raises(McigError, match=msg):
-            make(0, srrd, par)
+    # shapes without a closed form: Marsaglia & Tsang with 6 tries of 3 uniforms (+ 1 below shape 1), + the sign
+    g = make(0, 5, (2.3, 0.5))
+    assert "#define MCIG_SRRD_GENA 1" in g and "#define MCIG_SRRD_GENB 0" in g and "#define MCIG_SRRD_NU 19" in g and "#define MCIG_SRRD_SHA 0x1.2666666666666p+1" in g
+    assert "#define MCIG_SRRD_NU 20" in make(0, 5, (0.3, 1.0)) and "#define MCIG_SRRD_NU 19" in make(0, 8, (2.5,))  # Chisq(2.5) = 2 Gamma(1.25)
+    f = make(0, 9, (3.0, 200.0))  # Fisher: Gamma(3/2) by the closed form (1 + 2 uniforms), Gamma(100) by the test
+    assert "#define MCIG_SRRD_GENA 0" in f and "#define MCIG_SRRD_GENB 1" in f and "#define MCIG_SRRD_K2A 3" in f and "#define MCIG_SRRD_NU 22" in f
+    assert "MCIG_SRRD_GENA" not in make(0, 5, (2.5, 0.5))
     for srrd, par, msg in ((5, (2.0,), "takes 2 parameter"), (2, (1.0, 2.0), "takes 1 parameter"), (0, (1.0,), "takes 0 parameter"), (3, (0.0,), "positive"),
                            (7, (0.1, -1.0), "positive")):
         with pytest.raises(McigError, match=msg):

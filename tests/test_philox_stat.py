@@ -225,6 +225,10 @@ PARAM_LAWS = [  # (SRRDType, parameters, scipy law of the value (two-sided) or o
     # the default-parameter closed forms, through the same check
     (2, (), "t", dict(df=1.0), False), (4, (), "expon", dict(), True), (7, (), "lognorm", dict(s=1.0), True), (8, (), "chi2", dict(df=1.0), True),
     (9, (), "f", dict(dfn=1.0, dfd=1.0), True),
+    # shapes without a closed form: Marsaglia & Tsang's test with a fixed number of tries (srrd_gamma_mt)
+    (5, (2.3, 0.5), "gamma", dict(a=2.3, scale=0.5), True), (5, (0.3, 1.0), "gamma", dict(a=0.3), True), (5, (1.0001, 1.0), "gamma", dict(a=1.0001), True),
+    (5, (100.25, 0.01), "gamma", dict(a=100.25, scale=0.01), True), (8, (2.5,), "chi2", dict(df=2.5), True), (9, (3.0, 200.0), "f", dict(dfn=3.0, dfd=200.0), True),
+    (9, (2.7, 4.1), "f", dict(dfn=2.7, dfd=4.1), True),
 ]
 
 
@@ -256,19 +260,18 @@ def test_parameterised_proposals_follow_their_law(srrd, par, law, kw, positive, 
     assert ks.pvalue > 1e-4, (srrd, par, ks)
 
 
-def test_parameterised_proposals_without_fixed_count_sampler_are_refused(mcig):
+def test_parameterised_proposals_argument_checks(mcig):
     from mcintegratorplusplus_b200._capi import McigError
     mci = mcig.MCI(2)
     mci.setRngMode(0)
     mci.addSamplingFunction(mcig.Gauss(2))
     mci.addObservable(mcig.XND(2), 0, 1)
-    mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.3, 1.0))
-    with pytest.raises(McigError, match="multiples of 1/2"):
-        mci.prebuild()
     with pytest.raises(McigError, match="takes 2 parameter"):
         mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.0,))
     with pytest.raises(McigError, match="positive"):
         mci.setTrialMove(mcig.SRRDType.Student, 0, params=(-1.0,))
+    mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.3, 1.0))  # no closed form: fixed-count Marsaglia-Tsang in the Philox modes
+    mci.prebuild()
     mci.setRngMode(2)  # replay mode consumes the libstdc++ outputs of any parameter set
     mci.setTrialMove(mcig.SRRDType.Gamma, 0, params=(2.3, 1.0))
     mci.prebuild()
