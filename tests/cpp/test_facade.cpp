@@ -284,14 +284,16 @@ static void test_gpu()
         mci.integrate(32768, avg, err, true, false);
         for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
         assert(fabs(mci.getAcceptanceRate() - 0.5) < 0.05);
-        // symmetrised gamma with half-integer shape; shapes without a fixed-count sampler are refused in the Philox modes, asymmetric objects always
+        // symmetrised gamma with half-integer shape (closed form), then with a general shape (fixed-count Marsaglia-Tsang); asymmetric objects are refused
         auto gam = SymmetrizedPRRD<std::gamma_distribution<double>>(std::gamma_distribution<double>(2.5, 0.5));
         mci.setTrialMove(GammaAllMove(3, 0.3, &gam));
         assert(mci.getTrialMove().getSRRDParams().size() == 2);
         mci.integrate(32768, avg, err, false, false);
         for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
         auto gam2 = SymmetrizedPRRD<std::gamma_distribution<double>>(std::gamma_distribution<double>(2.3, 0.5));
-        assert(throws<std::invalid_argument>([&] { mci.setTrialMove(GammaAllMove(3, 0.3, &gam2)); mci.integrate(1024, avg, err, false, false); }));
+        mci.setTrialMove(GammaAllMove(3, 0.3, &gam2));
+        mci.integrate(32768, avg, err, false, false);
+        for (int i = 0; i < 4; ++i) { assert(fabs(avg[i] - 0.5) < 3.5*err[i]); }
         // the reference's vec-move clone drops the distribution (include/mci/SRRDVecMove.hpp:30-33): MCI holds a default-parameter move
         GammaVecMove gv(3, 1, 0.8, &gam);
         assert(gv.getSRRDParams().size() == 2);
