@@ -757,10 +757,12 @@ __global__ void fcblocker_kernel(const double * __restrict__ data, i64 n, i64 nc
 }
 
 // short series (the 100-sample chunks of the decorrelation loop): one warp stages its 32 chains in shared memory [n][32] once
+// stop: flag of a device-resident control loop (CalibCtl::done), or nullptr -- iterations enqueued behind the loop's end leave the previous results in place
 __global__ void __launch_bounds__(32) fcblocker_smem_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one, double * __restrict__ wavg,
-                                                            double * __restrict__ werr)
+                                                            double * __restrict__ werr, const int * __restrict__ stop)
 {
     extern __shared__ double fc_tile[];
+    if (stop != nullptr && *stop != 0) { return; }
     const i64 col = (i64)blockIdx.x*32 + threadIdx.x;
     const bool live = col < ncol;
     for (i64 i = 0; i < n; ++i) { fc_tile[i*32 + threadIdx.x] = live ? __ldcs(data + i*ncol + col) : 0.; }
@@ -776,9 +778,10 @@ __global__ void __launch_bounds__(32) fcblocker_smem_kernel(const double * __res
 // chains from the shared tile and warp 0 runs the plateau search. Every block sum is still accumulated in the reference's order.
 template <int NW>
 __global__ void __launch_bounds__(32*NW, 3) fcblocker_smem_par_kernel(const double * __restrict__ data, i64 n, i64 ncol, int nobs_is_one,
-                                                                  double * __restrict__ wavg, double * __restrict__ werr)
+                                                                  double * __restrict__ wavg, double * __restrict__ werr, const int * __restrict__ stop)
 {
     extern __shared__ double fc_tile[];
+    if (stop != nullptr && *stop != 0) { return; } // (block-uniform: before the first barrier)
     double * const st = fc_tile + n*32; // [90][32] partition statistics
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     const i64 col = (i64)blockIdx.x*32 + lane;
