@@ -313,6 +313,27 @@ def test_dynamic_equals_static_in_philox_mode(mcig):
         assert np.array_equal(np.asarray(a), np.asarray(b))
 
 
+def test_forced_dynamic_scheduling_of_a_small_job_uses_the_whole_gpu(mcig):
+    """setDynamicScheduling(1) on a job of fewer walker blocks than SMs once launched ONE persistent CTA (grid = floor(blocks / SMs) * SMs = 0 -> 1):
+    correct but 70 times slower than the static launch (profiles/r02bd_ws_thin.log). Every block is resident now: within a factor of the static launch,
+    and the same numbers."""
+    res = []
+    for dyn in (0, 1):
+        mci = mcig.MCI(3)
+        mci.setRngMode(0)
+        mci.setSeed(11)
+        mci.setNWalkers(8192)
+        mci.addSamplingFunction(mcig.ThreeDimGaussianPDF())
+        mci.addObservable(mcig.XSquared(), 0, 1)
+        mci.setMRT2Step(1.0)
+        mci.setDynamicScheduling(dyn)
+        mci.integrate(20000, False, False)
+        avg, err = mci.integrate(20000, False, False)
+        res.append((avg[0], mci.timings()["walk_ms"]))
+    assert res[0][0] == res[1][0]
+    assert res[1][1] < 4.0*res[0][1], res
+
+
 def test_file_dumps_match_reference_text(mcig, tmp_path):
     """storeObservablesOnFile / storeWalkerPositionsOnFile (src/MCIntegrator.cpp:495-542): the text the device path writes for walker
     0 in replay mode equals, character for character, what the reference wrote for the same run (tests/golden/dump_*.txt)."""
