@@ -261,6 +261,11 @@ def make_mci(m, rank, world, walkers=WALKERS_PER_GPU, device=None):
 C3_NDIMS = (1, 2, 4, 8, 16, 32, 64)
 
 
+# DRAM bytes of the C4 estimator stage (65536 chains x 2^14 samples = 8.59 GB of series), summed over its kernels: profiles/r02bf_c4_launches_ncu.csv
+C4_DRAM_BYTES = {"MJBlocker": 8591.4e6 + 179.8e6 + 184.6e6 + 4.0e6 + 16.3e6 + 0.7e6,   # mj_segments_tiled + mj_merge + mj_finish
+                 "FCBlocker": 8590.0e6 + 632.3e6 + 2.1e6 + 662.8e6 + 6.0e6 + 47.3e6 + 2.7e6}  # fc_split_prefix + fc_seg_scan + fc_part_stats + fc_final
+
+
 def c3_mci(m, move, nd, W, local):
     """BASELINE configs[2]: ExpNDPDF + XND with BlockAccumulator(20); `vec` is the reference's own single-particle sweep
     (benchmark/bench_throughput_ndim_single/main.cpp:26-50), `all` its all-move twin, `multistep` MultiStepMove(ndim sub-steps of a
@@ -362,7 +367,11 @@ def secondary_c4(m, local, pool):
         rows.append({"estimator": label, "walkers": W, "n_per_chain": nmc, "series_GB": nbytes/1e9, "walk_ms": w_ms, "estim_ms": e_ms,
                      "walk_steps_per_s": W*nmc/(w_ms*1e-3), "walk_store_GBps": nbytes/(w_ms*1e-3)/1e9, "avg": float(avg[0]), "err": float(err[0]),
                      "roofline": {"bound": "hbm", "achieved": nbytes/(e_ms*1e-3)/1e9, "peak": peak, "unit": "GB/s", "frac": nbytes/(e_ms*1e-3)/1e9/peak,
-                                  "peak_source": src, "algorithmic_bytes": "8 B per stored sample: one read of the series (the mean comes from the walk's running sum)"}})
+                                  "peak_source": src, "algorithmic_bytes": "8 B per stored sample: one read of the series (the mean comes from the walk's running sum)",
+                                  "traffic": C4_DRAM_BYTES[label],
+                                  "traffic_note": "dram__bytes_read + dram__bytes_write of the estimator's kernels for this series, ncu launch list "
+                                                  "profiles/r02bf_c4_launches_ncu.csv (not re-measured inside bench.py): the series is read exactly once (8.59 GB), "
+                                                  "the rest is the per-segment partial results; the walk that stages it writes 8.57 GB and reads 2 MB"}})
         del mci
     out["in_hbm"] = rows
     # (b) series larger than HBM
