@@ -304,7 +304,9 @@ def c3_work(move, nd):
         return 23 + nd, 1
     if move == "all":    # (ndim+1) uniforms + 2 ndim proposal + 2 ndim proto sums + 1 + exp 17 + compare 1 + ndim accumulate
         return (nd + 1) + 2*nd + 2*nd + 1 + 17 + 1 + nd, (nd + 1 + 3)//4
-    return 28*nd + 64, nd + 1  # MultiStepMove: 23 per sub-step + outer test, one block per sub-step + one for the outer accept draw
+    # MultiStepMove: 23 per sub-step + outer test; Philox blocks: four sub-steps share one draw group of 12 values = 3 blocks, the last ndim % 4 sub-steps
+    # and the outer accept uniform a group of 3 (ndim % 4) + 1 values (device/mcig_device.cuh: MCIG_MS_QUADS)
+    return 28*nd + 64, 3*(nd//4) + (3*(nd % 4) + 1 + 3)//4
 
 
 def secondary_c3(m, local, peaks, philox_peak, pool):
@@ -326,6 +328,10 @@ def secondary_c3(m, local, peaks, philox_peak, pool):
             row = {"ndim": nd, "steps_per_s": sps, "walk_ms": best["walk_ms"], "estim_ms": best["estim_ms"], "nmc": nmc, "acceptance": mci.getAcceptanceRate(),
                    "roofline": {"bound": "fp64_issue", "fp64_instr_per_step": instr, "achieved": instr*sps/1e9, "peak": peaks[0]/1e9, "unit": "GFP64inst/s",
                                 "frac": instr*sps/peaks[0], "philox_blocks_per_step": blocks, "rng_frac": blocks*sps/philox_peak}}
+            if move == "multistep":
+                row["roofline"]["note"] = ("fp64_instr_per_step is SURVEY.md §8d's ALGORITHMIC count of the reference's expression (one exp per sub-step, three exp and a "
+                                           "division per outer step); the kernel decides sub-steps and the outer step in log form through the FP32 pre-filter and executes far "
+                                           "fewer FP64 instructions, so this fraction overstates the pipe's load (it exceeds 1 at ndim 1): the bound that holds is rng_frac")
             if pool is not None:
                 nmc_cpu = max(2000, int({"vec": 2.4e7/(1 + nd/6.0), "all": 2.4e7/(1 + nd/1.5)}.get(move, 2.4e7/(1 + 6.0*nd)))//20*20)  # ~0.2-1 s per chain
                 v, wall, _ = pool.run(c3_kw(move, nd), nmc_cpu)
