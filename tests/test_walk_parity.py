@@ -174,6 +174,48 @@ def test_c3_shapes_philox_placements_agree(name, mcig):
     assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-12*scale
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("ndim,veclen,nsub", [(6, 1, 0), (4, 1, 0), (5, 1, 7), (6, 3, 5), (24, 1, 0), (3, 1, 1)])
+def test_multistep_quad_draw_groups_keep_the_stream_properties(ndim, veclen, nsub, mode, mcig):
+    """MultiStepMove in the Philox modes packs four sub-steps into one draw group (3 Philox blocks instead of 4) and the outer accept uniform into the
+    group of the last nsteps % 4 sub-steps (device/mcig_device.cuh: MCIG_MS_QUADS). The stream properties must survive for every sub-step count and
+    vector length: two launches continue one launch's streams, the dynamically scheduled kernel equals the static one, a shard of the walkers
+    reproduces its walkers of the full job, and the state placements agree (shared = global bit for bit, registers to the accept decisions)."""
+    spec = dict(ndim=ndim, seed=77, pdf_id=orc.PDF_GAUSS, obs=[(orc.OBS_XND, 0, 1)], nmc=1200, move_type=orc.MOVE_MULTISTEP, veclen=veclen,
+                ms_nsteps=nsub, ms_sub_pdf_id=orc.PDF_EXPND, steps=(0.6,), x0=[0.1*(-1)**j for j in range(ndim)])
+
+    def run(placement=None, parts=(1200,), dyn=-1, shard=None):
+        mci = build_mci(mcig, spec, nwalkers=64 if shard else 192, mode=mode, placement=placement)
+        if shard:
+            mci.setNWalkers(64, global_offset=64, total=192)
+        mci.setLazyAccumulation(0)
+        mci.setDynamicScheduling(dyn)
+        for n in parts:
+            avg, err = mci.integrate(n, False, False)
+        W = 64 if shard else 192
+        return avg.copy(), mci.getAcceptanceRate(), [list(mci.getX(walker=w)) for w in (0, 33, W - 1)]
+
+    base = run()
+    # the same streams whatever the launch chunking (400 + 800 steps: not multiples of the sub-step count or of four)
+    assert run(parts=(400, 800))[2] == base[2]
+    assert run(parts=(1, 1199))[2] == base[2]
+    # dynamic chunk scheduling (register kernels): same numbers
+    if ndim <= 8:
+        d = run(dyn=1)
+        assert d[2] == base[2] and d[1] == base[1]
+    # a shard reproduces its walkers
+    sh = run(shard=True)
+    full = build_mci(mcig, spec, nwalkers=192, mode=mode)
+    full.setLazyAccumulation(0)
+    full.integrate(1200, False, False)
+    assert sh[2][0] == list(full.getX(walker=64)) and sh[2][2] == list(full.getX(walker=127))
+    # placements
+    outs = [run(placement=pl) for pl in (0, 1, 2)]
+    assert outs[1][2] == outs[2][2] and outs[1][1] == outs[2][1] and np.array_equal(outs[1][0], outs[2][0])
+    assert outs[0][1] == outs[1][1]
+    assert np.allclose(outs[0][2], outs[1][2], rtol=1e-12, atol=1e-14)
+
+
 def test_accept_sequence_and_trajectory_bit_exact(mcig, oracle):
     """Every step: positions from a Full XND accumulator vs the trajectory implied by the oracle's draws + accept bits."""
     nmc = 20000
