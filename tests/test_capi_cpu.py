@@ -247,3 +247,29 @@ def test_multistep_cold_position_rules(mcig):
     assert "MS_COLD_X = true" in s32 and "RegStore<32>" in s32  # 32 sums stay in registers
     assert "MS_COLD_X = true" in make(64, sub=False) and "MS_COLD_X = false" in make(16)
     assert "MS_COLD_X = true" in make(64, w=4096)  # (small jobs: whatever block size fills the machine best; must compile)
+
+
+def test_multistep_quad_draw_groups_host_rules(mcig, monkeypatch):
+    """MultiStepMove in the Philox modes packs four sub-steps into one draw group; the HOST decides (groups_per_step() must agree with the kernels), so
+    the switch travels inside the generated source: on in both Philox modes, off in replay mode (the reference's draws are consumed one by one), off
+    with the measurement knob and with the pairwise sub-step experiment (which draws per sub-step). Other moves carry no switch at all."""
+    def make(mode, move=None, ndim=6):
+        mci = mcig.MCI(ndim)
+        mci.setRngMode(mode)
+        mci.addSamplingFunction(mcig.Gauss(ndim))
+        mci.addObservable(mcig.XND(ndim), 0, 1)
+        if move is None:
+            mci.setTrialMove(mcig.MoveType.MultiStep, 1, sub_pdfs=[mcig.ExpNDPDF(ndim)])
+        else:
+            mci.setTrialMove(move)
+        mci.prebuild()
+        return mci.kernelSource()
+
+    assert "#define MCIG_MS_QUADS 1" in make(0) and "#define MCIG_MS_QUADS 1" in make(1)
+    assert "#define MCIG_MS_QUADS 0" in make(2)
+    assert "MCIG_MS_QUADS" not in make(0, mcig.MoveType.All) and "MCIG_MS_QUADS" not in make(0, mcig.MoveType.Vec)
+    monkeypatch.setenv("MCIG_MS_QUADS", "0")
+    assert "#define MCIG_MS_QUADS 0" in make(0)
+    monkeypatch.delenv("MCIG_MS_QUADS")
+    monkeypatch.setenv("MCIG_JIT_DEFINES", "MCIG_MS_PAIR=1")
+    assert "#define MCIG_MS_QUADS 0" in make(0, ndim=24)
